@@ -1,0 +1,75 @@
+"""The C oracle (Riccati recursion) against the numpy oracle (dense KKT) and against the decoded acados run."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import nmpc_oracle as o
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+P = np.array([[o.MASS, o.GRAVITY_ACC]])
+
+
+def _max_err(series, g, name):
+    st, v = g[name + '_step'], g[name]
+    return float(np.max(np.abs(series[st] - v)))
+
+
+@pytest.mark.parametrize('model,tag,lo', [(co.MODEL_FORCE, 'force', 0), (co.MODEL_JERK, 'jerk', 500)])
+def test_c_oracle_reproduces_acados_run(model, tag, lo):
+    g = np.load(os.path.join(GOLD, f'acados_{tag}.npz'))
+    eps = o.main_py_noise()[lo:lo + 500]
+    r = co.closed_loop(co.default_opts(model), o.gen_circle_traj(), np.array([[1.0, 0, 0, 0.62]]), eps[:, None], P, P, 500)
+    assert np.all(r['status'] == 0)
+    assert _max_err(r['U_plant'][0, :, 0], g, 'theta') < 5e-7
+    assert _max_err(r['U_plant'][0, :, 1], g, 'Fd') < 1e-7
+    for name, col in (('px', 0), ('pz', 1), ('vx', 2), ('vz', 3)):
+        assert _max_err(r['Xsim'][0, :, col], g, name) < 1e-7
+
+
+@pytest.mark.parametrize('model', [co.MODEL_FORCE, co.MODEL_JERK])
+def test_c_vs_numpy_single_solves(model):
+    """Random x0 / reference phases, some with bounds active; compare whole solutions and integer outputs."""
+    rng = np.random.default_rng(5)
+    spec = o.force_ocp() if model == co.MODEL_FORCE else o.jerk_ocp()
+    nx, nu, N = spec.nx, spec.nu, spec.N
+    B = 6
+    x0s, yrefs = [], []
+    for i in range(B):
+        ref = o.gen_circle_traj(radius=rng.uniform(0.5, 1.0), center=rng.uniform(-0.15, 0.15, 2), phase=rng.uniform(0, 2 * np.pi))
+        st = rng.integers(0, 400)
+        x0 = ref[st, :4] + rng.uniform(-0.08, 0.08, 4)
+        if model == co.MODEL_JERK:
+            x0 = np.hstack([x0, [rng.uniform(-1, 1), o.GRAVITY_ACC + rng.uniform(-1, 1)]])
+            y = np.hstack([ref[st:st + N, :8].ravel(), ref[st + N, :6]])
+        else:
+            y = np.hstack([ref[st:st + N, :6].ravel(), ref[st + N, :4]])
+        x0s.append(x0); yrefs.append(y)
+    x0s, yrefs = np.array(x0s), np.array(yrefs)
+    rc = co.solve_batch(co.default_opts(model), x0s, yrefs, np.repeat(P, B, 0))
+    for i in range(B):
+        sol = o.OracleOcpSolver(spec)
+        ny = nx + nu
+        for k in range(N):
+            sol.set(k, 'yref', yrefs[i, k * ny:(k + 1) * ny])
+        sol.set(N, 'yref', yrefs[i, N * ny:])
+        sol.set(0, 'lbx', x0s[i])
+        st = sol.solve()
+        assert st == rc['status'][i]
+        assert sol.sqp_iter == rc['sqp_iter'][i] and sol.qp_iter == rc['qp_iter'][i]
+        np.testing.assert_allclose(rc['u'][i], sol.u, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(rc['x'][i], sol.x, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(rc['pi'][i], sol.pi, rtol=0, atol=1e-8)
+
+
+def test_threads_do_not_change_results():
+    rng = np.random.default_rng(1)
+    B = 16
+    ref = o.gen_circle_traj()
+    x0 = ref[0, :4] + rng.uniform(-0.05, 0.05, (B, 4))
+    noise = rng.normal(0, 0.01, (20, B))
+    pp = np.repeat(P, B, 0)
+    a = co.closed_loop(co.default_opts(co.MODEL_FORCE), ref, x0, noise, pp, pp, 20, nthreads=1)
+    b = co.closed_loop(co.default_opts(co.MODEL_FORCE), ref, x0, noise, pp, pp, 20, nthreads=4)
+    assert np.array_equal(a['Xsim'], b['Xsim']) and np.array_equal(a['qp_iter'], b['qp_iter'])
