@@ -1,0 +1,166 @@
+/* bnmpc - B200-native batched NMPC solver: C-ABI of the drop-in boundary.
+ *
+ * This header is the whole boundary between the reference-facing host code (Python, ctypes) and the CUDA
+ * implementation (libbnmpc.so, sm_100a).  Plain C types only.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference repo BroilerCompiler/drone-attitude-control); the arithmetic behind
+ * those reference calls lives in acados / HPIPM / BLASFEO / CasADi-generated C, reached through
+ * acados_template.AcadosOcpSolver / AcadosSimSolver (ctypes) - this library replaces that stack for this path.
+ *
+ * One handle <-> one device <-> one CUDA stream <-> `batch` independent OCP instances.  Not thread-safe.
+ * All calls are asynchronous on the handle's stream except those that copy to host memory (they synchronise).
+ * The handle owns every workspace; the caller owns every buffer it passes; no pointer is retained after a call
+ * returns.  Return value: 0 on success, negative BNMPC_E_* on API errors (message via bnmpc_last_error()).
+ * Per-instance solver outcomes use the acados status codes (reference src/Readme.md:14-20).
+ *
+ * Layouts.  "AoS" buffers are [batch][dim] row-major doubles (one acados-style vector per instance).
+ * "Batch-minor" buffers are [...][dim][batch] doubles with the batch index contiguous (coalesced in HBM).
+ * `on_device` != 0 means the pointer is device memory of the handle's device; 0 means host memory (pinned host
+ * memory makes the copy asynchronous).  All API arrays are FP64 regardless of the compute precision.
+ */
+#ifndef BNMPC_H
+#define BNMPC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNMPC_VERSION 100
+
+/* models (reference src/force_model/dynamics.py:12-47, src/jerk_model/dynamics.py:12-52).  The *_DENSE variants
+ * solve the same OCP without exploiting the x/z block structure (generic coupled path; cross-check). */
+#define BNMPC_MODEL_FORCE 0
+#define BNMPC_MODEL_JERK 1
+#define BNMPC_MODEL_FORCE_DENSE 2
+#define BNMPC_MODEL_JERK_DENSE 3
+
+#define BNMPC_FP64 0
+#define BNMPC_FP32 1
+
+/* acados return values, reference src/Readme.md:14-20 */
+#define BNMPC_SUCCESS 0
+#define BNMPC_FAILURE 1      /* NaN/Inf in x0, yref or p */
+#define BNMPC_MAXITER 2      /* SQP iteration cap (or, in RTI mode, QP iteration cap) */
+#define BNMPC_MINSTEP 3
+#define BNMPC_QP_FAILURE 4   /* QP solver: minimum step / NaN */
+
+/* API error codes */
+#define BNMPC_E_ARG (-1)
+#define BNMPC_E_FIELD (-2)
+#define BNMPC_E_STAGE (-3)
+#define BNMPC_E_CUDA (-4)
+#define BNMPC_E_UNSUPPORTED (-5)
+
+/* fields of set/get: reference `ocp_solver.set(stage, name, vec)` / `.get(stage, name)`
+ * (src/force_model/controller.py:30-39, src/force_model/ocp.py:120-122) */
+#define BNMPC_F_X 0      /* 'x'    stage 0..N,   dim nx   (get/set) */
+#define BNMPC_F_U 1      /* 'u'    stage 0..N-1, dim nu   (get/set) */
+#define BNMPC_F_YREF 2   /* 'yref' stage 0..N-1 dim nx+nu, stage N dim nx (set/get) */
+#define BNMPC_F_LBX 3    /* 'lbx'  stage 0 only: x0 embedding (controller.py:30) */
+#define BNMPC_F_UBX 4    /* 'ubx'  stage 0 only: x0 embedding (controller.py:31); must equal lbx */
+#define BNMPC_F_P 5      /* 'p'    stage ignored, dim 2 = (mass, g) of the controller model (north-star extension) */
+#define BNMPC_F_PI 6     /* 'pi'   stage 0..N-1, dim nx   (get) */
+#define BNMPC_F_LAM 7    /* 'lam'  stage 0..N-1, dim 2*(nu[+nx]) = [lbu, lbx, ubu, ubx] multipliers (get) */
+
+/* per-instance int32 statistics: reference `ocp_solver.get_stats(name)` */
+#define BNMPC_STAT_STATUS 0
+#define BNMPC_STAT_SQP_ITER 1
+#define BNMPC_STAT_QP_ITER 2
+
+typedef struct bnmpc_config {
+    int32_t model;          /* BNMPC_MODEL_* */
+    int32_t horizon;        /* N_horizon (reference src/params.py:121) */
+    int32_t precision;      /* BNMPC_FP64 | BNMPC_FP32 */
+    int32_t erk_stages;     /* OCP integrator stages, one step per interval: force 4 (stands in for IRK: exact for the
+                               affine model, src/force_model/ocp.py:85), jerk 1 (src/jerk_model/ocp.py:86-87) */
+    int32_t sqp_max_iter;   /* acados nlp_solver_max_iter default 100 (nlp_solver_type SQP, src/force_model/ocp.py:86) */
+    int32_t qp_max_iter;    /* acados qp_solver_iter_max default 50 */
+    int32_t rti;            /* 1: one QP per solve, no NLP residual test (SQP_RTI of the north-star) */
+    int32_t threads_per_block; /* 0 = library default */
+    double dt;              /* interval length, tf / N (src/params.py:116, src/force_model/ocp.py:93) */
+    double W[12];           /* diag of cost.W, order [x; u] (src/force_model/ocp.py:38-47) */
+    double W_e[8];          /* diag of cost.W_e */
+    double lbx[8], ubx[8];  /* state box, stages 1..N-1 (src/force_model/ocp.py:72-76) */
+    double lbu[4], ubu[4];  /* input box, stages 0..N-1 (src/force_model/ocp.py:62-67) */
+    double tol[4];          /* NLP tolerances stat, eq, ineq, comp (acados default 1e-6) */
+    double qp_tol[4];       /* QP tolerances (acados passes the NLP tolerances on to HPIPM) */
+    double mu0, thr0, alpha_min, lam_min, t_min; /* HPIPM arguments as acados sets them */
+    /* plant integrator = AcadosSim of src/plant.py (src/force_model/ocp.py:98-104, src/jerk_model/ocp.py:97-104) */
+    int32_t sim_erk_stages; /* force path 4, jerk path 1 */
+    int32_t sim_substeps;   /* force path 1, jerk path ctrls_per_sample = 10 */
+    double sim_dt;          /* force path dt, jerk path dt_conv */
+} bnmpc_config;
+
+/* Fills *cfg with the reference's configuration of `model` (OCP.create_ocp + create_ocp_solver + create_simulator). */
+int bnmpc_config_default(int model, bnmpc_config* cfg);
+
+/* AcadosOcpSolver(ocp) + AcadosSimSolver(sim)  (src/force_model/ocp.py:95-96,104): allocates everything. */
+int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle);
+int bnmpc_destroy(void* handle);
+/* cudaStream_t to run on (default: a stream created by the handle). */
+int bnmpc_set_stream(void* handle, void* cuda_stream);
+int bnmpc_synchronize(void* handle);
+/* dimensions of the configured model: nx, nu, ny (=nx+nu), ny_e (=nx), N, np, number of blocks */
+int bnmpc_dims(void* handle, int32_t dims[7]);
+/* workspace bytes held by the handle */
+int64_t bnmpc_workspace_bytes(void* handle);
+
+/* ocp_solver.set(stage, field, value) for all instances at once; value is AoS [batch][dim]. */
+int bnmpc_set(void* handle, int stage, int field, const double* value, int on_device);
+/* ocp_solver.get(stage, field); out is AoS [batch][dim]. */
+int bnmpc_get(void* handle, int stage, int field, double* out, int on_device);
+/* OCP.set_up_ocp in one call (src/force_model/ocp.py:117-122): AoS [batch][N*ny + ny_e] = yref_0 .. yref_{N-1}, yref_N */
+int bnmpc_set_yref_all(void* handle, const double* value, int on_device);
+/* zero the primal iterate and multipliers (state of a freshly created acados solver) */
+int bnmpc_reset(void* handle);
+/* ocp_solver.solve() (src/force_model/controller.py:32): one acados-style SQP run per instance from the stored
+ * iterate with the stored x0 / yref / p.  Per-instance status via bnmpc_get_stats. */
+int bnmpc_solve(void* handle);
+/* ocp_solver.get_stats / status: int32 [batch] */
+int bnmpc_get_stats(void* handle, int which, int32_t* out, int on_device);
+
+/* OCP.simulate_next_x without the noise draw (src/force_model/ocp.py:106-112, src/jerk_model/ocp.py:106-113):
+ * x AoS [batch][4], u AoS [batch][sim_substeps][2] = (theta, Fd) per sub-step, p_plant AoS [batch][2] or NULL
+ * (nominal), eps [batch] or NULL added to all states of an instance (the np.random.normal draw, :114-115). */
+int bnmpc_sim_step(void* handle, const double* x, const double* u, const double* p_plant, const double* eps,
+                   double* x_next, int on_device);
+
+/* Fused closed loop = follow_trajectory (src/force_model/controller.py:8-56, src/jerk_model/controller.py:8-58) for
+ * all instances, device-resident between steps.  All pointers are DEVICE pointers, batch-minor layout. */
+typedef struct bnmpc_closed_loop_args {
+    int32_t n_steps;        /* control steps to run in this call */
+    int32_t first_step;     /* index of the first step (row offset into ref, noise and the logs) */
+    int32_t ref_rows;       /* rows of ref; needs first_step + n_steps + N <= ref_rows */
+    int32_t ref_shared;     /* 1: ref is one [rows][8] table for all instances, 0: [rows][8][batch] */
+    int32_t log_stride;     /* number of steps the log arrays were allocated for (>= first_step + n_steps) */
+    int32_t reserved;
+    const double* ref;      /* gen_circle_traj layout, 8 columns [px pz vx vz ax az+g 0 0] (src/generate_trajectory.py:7-28) */
+    const double* noise;    /* [log_stride][batch] or NULL: eps of step s for instance i (src/force_model/ocp.py:114) */
+    /* optional logs (NULL to skip), [log_stride(+1)][dim][batch] */
+    double* Xsim;           /* [log_stride+1][4][batch]; row first_step must hold the current state on entry if non-NULL */
+    double* U_plant;        /* [log_stride][2][batch]  (theta, Fd) of the last sub-step (controller.py:44 / jerk :46) */
+    double* U_ctrl;         /* [log_stride][2][batch]  u0 of the OCP */
+    double* a_log;          /* [log_stride][2][batch]  force: u0/m (controller.py:38), jerk: a_i (jerk controller.py:45) */
+    int32_t* status;        /* [log_stride][batch] */
+    int32_t* qp_iter;       /* [log_stride][batch] */
+} bnmpc_closed_loop_args;
+
+/* start of follow_trajectory: Xsim[0] = x0, a_i = [0, g], closedLoopCost = 0, zero iterate.
+ * x0 [4][batch]; p_ctrl, p_plant [2][batch] (NULL = nominal mass 0.03277, g 9.81).  Device pointers. */
+int bnmpc_closed_loop_init(void* handle, const double* x0, const double* p_ctrl, const double* p_plant);
+int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* args);
+/* results so far: cost [batch] (closedLoopCost), abs_err [batch] (sum over steps of |pref-psim| over both position
+ * coordinates = calc_aed numerator, src/store_results.py:233-236), x [4][batch] current plant state, acc [2][batch]
+ * (jerk a_i).  Any pointer may be NULL.  Device pointers. */
+int bnmpc_closed_loop_state(void* handle, double* cost, double* abs_err, double* x, double* acc);
+
+/* number of kernels this library has launched on the handle since creation */
+int64_t bnmpc_launch_count(void* handle);
+const char* bnmpc_last_error(void);
+int bnmpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNMPC_H */
