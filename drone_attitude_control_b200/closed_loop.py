@@ -1,0 +1,104 @@
+"""Fused, device-resident closed loop for many drones: follow_trajectory of the reference
+(src/force_model/controller.py:8-56, src/jerk_model/controller.py:8-58) for `batch` instances at once.
+
+Per control step ONE kernel does, per instance: yref windowing (set_up_ocp), x0 embedding, the SQP/HPIPM solve,
+Converter.convert, the plant step (simulate_next_x) with the supplied noise draw, and the logged quantities.
+Plant state, carried acceleration (jerk model), cost and |error| sums stay on the device between steps.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ._lib import ClosedLoopArgs, check, lib
+from .acados_shim import BatchedAcadosOcpSolver
+from .params import ExperimentParameters
+
+p = ExperimentParameters()
+
+
+class BatchedClosedLoop:
+    def __init__(self, model='force', batch=1, device=0, precision='fp64', N_horizon=None, rti=False, **overrides):
+        self.solver = BatchedAcadosOcpSolver(model, batch=batch, device=device, precision=precision,
+                                             N_horizon=p.N_horizon if N_horizon is None else N_horizon, rti=rti,
+                                             numpy_io=False, **overrides)
+        self.batch, self.device, self.N = self.solver.batch, self.solver.device, self.solver.N
+        self.step = 0
+        self._logs = {}
+
+    def _dev(self, t, shape=None, dtype=torch.float64):
+        if t is None:
+            return None
+        t = torch.as_tensor(t, dtype=dtype).to(self.device).contiguous()
+        if shape is not None and tuple(t.shape) != tuple(shape):
+            raise ValueError(f'expected shape {tuple(shape)}, got {tuple(t.shape)}')
+        return t
+
+    def init(self, x0, ref, noise=None, p_ctrl=None, p_plant=None, n_steps=None, log=True):
+        """x0 [4, B]; ref [rows, 8] (shared) or [rows, 8, B]; noise [n_steps, B] or None; p_ctrl / p_plant [2, B] or None
+        (nominal mass 0.03277, g 9.81).  All batch-minor, float64."""
+        B = self.batch
+        self.x0 = self._dev(x0, (4, B))
+        self.ref = self._dev(ref)
+        if self.ref.dim() == 2:
+            assert self.ref.shape[1] == 8
+        else:
+            assert tuple(self.ref.shape[1:]) == (8, B)
+        self.n_steps = int(n_steps if n_steps is not None else self.ref.shape[0] - self.N)
+        assert self.ref.shape[0] >= self.n_steps + self.N
+        self.noise = self._dev(noise, (self.n_steps, B)) if noise is not None else None
+        self.p_ctrl = self._dev(p_ctrl, (2, B)) if p_ctrl is not None else None
+        self.p_plant = self._dev(p_plant, (2, B)) if p_plant is not None else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(lib().bnmpc_closed_loop_init(self.solver.handle, ptr(self.x0), ptr(self.p_ctrl), ptr(self.p_plant)))
+        self.step = 0
+        self._logs = {}
+        if log:
+            S = self.n_steps
+            z = lambda *sh, dt=torch.float64: torch.zeros(sh, dtype=dt, device=self.device)
+            self._logs = dict(Xsim=z(S + 1, 4, B), U_plant=z(S, 2, B), U_ctrl=z(S, 2, B), a=z(S, 2, B),
+                              status=z(S, B, dt=torch.int32), qp_iter=z(S, B, dt=torch.int32))
+            self._logs['Xsim'][0] = self.x0
+        return self
+
+    def run(self, n_steps=None):
+        """Advance `n_steps` control steps (default: the rest); one kernel launch per step."""
+        n = self.n_steps - self.step if n_steps is None else int(n_steps)
+        a = ClosedLoopArgs()
+        a.n_steps, a.first_step, a.ref_rows = n, self.step, int(self.ref.shape[0])
+        a.ref_shared, a.log_stride = int(self.ref.dim() == 2), self.n_steps
+        a.ref = self.ref.data_ptr()
+        a.noise = self.noise.data_ptr() if self.noise is not None else None
+        L = self._logs
+        if L:
+            a.Xsim, a.U_plant, a.U_ctrl, a.a_log = (L[k].data_ptr() for k in ('Xsim', 'U_plant', 'U_ctrl', 'a'))
+            a.status, a.qp_iter = L['status'].data_ptr(), L['qp_iter'].data_ptr()
+        check(lib().bnmpc_closed_loop_run(self.solver.handle, C.byref(a)))
+        self.step += n
+        return self
+
+    def state(self):
+        """(closedLoopCost [B], sum |pref - psim| [B], plant state [4, B], carried acceleration [2, B]) so far"""
+        B = self.batch
+        z = lambda *sh: torch.empty(sh, dtype=torch.float64, device=self.device)
+        cost, err, x, acc = z(B), z(B), z(4, B), z(2, B)
+        check(lib().bnmpc_closed_loop_state(self.solver.handle, *(C.c_void_p(t.data_ptr()) for t in (cost, err, x, acc))))
+        return cost, err, x, acc
+
+    def results(self):
+        """Per-instance outputs in the reference's shapes: cost [B], AvgEucDist [B] (calc_aed over the steps run), and the
+        logs Xsim [B, S+1, 4], a [B, S, 2], U_opt_plant [B, S, 2] (+ U_ctrl, status, qp_iter)."""
+        cost, err, _, _ = self.state()
+        out = dict(cost=cost, aed=err / (2.0 * max(self.step, 1)))
+        for k, v in self._logs.items():
+            out[k] = v.permute(2, 0, 1) if v.dim() == 3 else v.t()
+        return out
+
+
+def follow_trajectory_batched(model, ref, x0, noise=None, p_ctrl=None, p_plant=None, n_steps=None, device=0, precision='fp64', **kw):
+    """follow_trajectory for B drones in one call; returns the dict of BatchedClosedLoop.results()."""
+    x0 = torch.as_tensor(x0, dtype=torch.float64)
+    loop = BatchedClosedLoop(model, batch=x0.shape[1], device=device, precision=precision, **kw)
+    loop.init(x0, ref, noise=noise, p_ctrl=p_ctrl, p_plant=p_plant, n_steps=n_steps)
+    loop.run()
+    return loop.results()

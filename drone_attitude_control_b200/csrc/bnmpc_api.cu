@@ -1,0 +1,501 @@
+// bnmpc_api.cu - the C-ABI of include/bnmpc.h: handle, workspace, staging, kernel launches.  No solver arithmetic here.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/bnmpc.h"
+#include "bnmpc_kernels.cuh"
+
+using namespace bnmpc;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define CK(call)                                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) return fail(BNMPC_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+struct Handle {
+    bnmpc_config cfg;
+    Opts opts;
+    const ModelOps* ops;
+    int batch, device, tpb;
+    cudaStream_t stream;
+    bool own_stream;
+    WsAny ws;
+    int rows;
+    size_t ws_bytes;
+    int32_t* ints;                 // status | sqp_iter | qp_iter | have_mult
+    double* stage[4];              // device staging buffers for host<->device AoS copies
+    size_t stage_cap[4];
+    // closed-loop state, stride Bp
+    size_t Bp;
+    double *xs, *acc, *cost, *abs_err, *p_plant;
+    int64_t launches;
+};
+
+const ModelOps* pick_ops(int model, int precision) {
+    switch (model) {
+    case BNMPC_MODEL_FORCE: return ops_force(precision);
+    case BNMPC_MODEL_JERK: return ops_jerk(precision);
+    case BNMPC_MODEL_FORCE_DENSE: return ops_force_dense(precision);
+    case BNMPC_MODEL_JERK_DENSE: return ops_jerk_dense(precision);
+    }
+    return nullptr;
+}
+
+Opts make_opts(const bnmpc_config& c) {
+    Opts o;
+    memset(&o, 0, sizeof(o));
+    o.N = c.horizon; o.erk_stages = c.erk_stages; o.sqp_max_iter = c.sqp_max_iter; o.qp_max_iter = c.qp_max_iter; o.rti = c.rti;
+    o.sim_erk_stages = c.sim_erk_stages; o.sim_substeps = c.sim_substeps; o.dt = c.dt; o.sim_dt = c.sim_dt;
+    memcpy(o.W, c.W, sizeof(o.W)); memcpy(o.W_e, c.W_e, sizeof(o.W_e));
+    memcpy(o.lbx, c.lbx, sizeof(o.lbx)); memcpy(o.ubx, c.ubx, sizeof(o.ubx));
+    memcpy(o.lbu, c.lbu, sizeof(o.lbu)); memcpy(o.ubu, c.ubu, sizeof(o.ubu));
+    memcpy(o.tol, c.tol, sizeof(o.tol)); memcpy(o.qp_tol, c.qp_tol, sizeof(o.qp_tol));
+    o.mu0 = c.mu0; o.thr0 = c.thr0; o.alpha_min = c.alpha_min; o.lam_min = c.lam_min; o.t_min = c.t_min;
+    return o;
+}
+
+int use_device(Handle* h) {
+    CK(cudaSetDevice(h->device));
+    return 0;
+}
+
+// device view of a caller buffer of `count` doubles: the pointer itself, or a staged copy of host memory
+int stage_in(Handle* h, int slot, const double* p, size_t count, int on_device, const double** out) {
+    if (on_device) { *out = p; return 0; }
+    if (h->stage_cap[slot] < count) {
+        if (h->stage[slot]) CK(cudaFree(h->stage[slot]));
+        h->stage[slot] = nullptr; h->stage_cap[slot] = 0;
+        CK(cudaMalloc(&h->stage[slot], count * sizeof(double)));
+        h->stage_cap[slot] = count;
+    }
+    CK(cudaMemcpyAsync(h->stage[slot], p, count * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    *out = h->stage[slot];
+    return 0;
+}
+
+int stage_out_begin(Handle* h, int slot, double* p, size_t count, int on_device, double** dev) {
+    if (on_device) { *dev = p; return 0; }
+    if (h->stage_cap[slot] < count) {
+        if (h->stage[slot]) CK(cudaFree(h->stage[slot]));
+        h->stage[slot] = nullptr; h->stage_cap[slot] = 0;
+        CK(cudaMalloc(&h->stage[slot], count * sizeof(double)));
+        h->stage_cap[slot] = count;
+    }
+    *dev = h->stage[slot];
+    return 0;
+}
+
+int stage_out_end(Handle* h, int slot, double* p, size_t count, int on_device) {
+    if (on_device) return 0;
+    CK(cudaMemcpyAsync(p, h->stage[slot], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+__global__ void k_sim_step(int B, int ns, int nsub, double hstep, const double* x, const double* u, const double* p_plant,
+                           const double* eps, double* xn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double xs[4], pp[2] = {0.03277, 9.81};
+#pragma unroll
+    for (int j = 0; j < 4; j++) xs[j] = x[(size_t)i * 4 + j];
+    if (p_plant) { pp[0] = p_plant[(size_t)i * 2]; pp[1] = p_plant[(size_t)i * 2 + 1]; }
+    for (int j = 0; j < nsub; j++) {
+        const double up[2] = {u[((size_t)i * nsub + j) * 2], u[((size_t)i * nsub + j) * 2 + 1]};
+        plant_step<double>(ns, pp, hstep, up, xs);
+    }
+    const double e = eps ? eps[i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) xn[(size_t)i * 4 + j] = xs[j] + e;
+}
+
+__global__ void k_loop_init(int B, size_t Bp, const double* x0, const double* p_ctrl, const double* p_plant, double* xs, double* acc,
+                            double* cost, double* abs_err, double* pp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+#pragma unroll
+    for (int j = 0; j < 4; j++) xs[(size_t)j * Bp + i] = x0[(size_t)j * B + i];
+    acc[i] = 0.0;                                             // jerk controller.py:23  a_i = [0, g]
+    acc[Bp + i] = p_ctrl ? p_ctrl[(size_t)B + i] : 9.81;
+    cost[i] = 0.0; abs_err[i] = 0.0;
+    pp[i] = p_plant ? p_plant[i] : 0.03277;
+    pp[Bp + i] = p_plant ? p_plant[(size_t)B + i] : 9.81;
+}
+
+__global__ void k_loop_state(int B, size_t Bp, const double* xs, const double* acc, const double* cost, const double* abs_err,
+                             double* o_cost, double* o_err, double* o_x, double* o_acc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    if (o_cost) o_cost[i] = cost[i];
+    if (o_err) o_err[i] = abs_err[i];
+    if (o_x) for (int j = 0; j < 4; j++) o_x[(size_t)j * B + i] = xs[(size_t)j * Bp + i];
+    if (o_acc) for (int j = 0; j < 2; j++) o_acc[(size_t)j * B + i] = acc[(size_t)j * Bp + i];
+}
+
+template <class T>
+__global__ void k_fma_peak(T* out, int iters) {
+    T a[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = T(threadIdx.x + i) * T(1e-3);
+    const T b = T(1.0000001), c = T(1e-7);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = a[i] * b + c;
+    }
+    T s = T(0);
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == T(-1)) out[0] = s;   // never true; keeps the chains alive
+}
+
+template <class T>
+int fma_peak(double* tflops) {
+    T* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(T)));
+    cudaDeviceProp pr;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaGetDeviceProperties(&pr, dev));
+    const int blocks = pr.multiProcessorCount * 8, tpb = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        CK(cudaEventRecord(e0));
+        k_fma_peak<T><<<blocks, tpb>>>(d, iters);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 64.0 * iters * (double)blocks * tpb;
+        if (rep > 0 && fl / (ms * 1e-3) * 1e-12 > best) best = fl / (ms * 1e-3) * 1e-12;
+    }
+    CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1)); CK(cudaFree(d));
+    *tflops = best;
+    return 0;
+}
+
+int default_tpb(const Handle* h) {
+    if (h->cfg.threads_per_block > 0) return (h->cfg.threads_per_block + 31) / 32 * 32;
+    // few instances: one warp per CTA spreads the warps over all SMs; many: larger CTAs
+    const size_t warps = h->ws.S / 32;
+    if (warps <= 148 * 8) return 32;
+    if (warps <= 148 * 32) return 64;
+    return 128;
+}
+
+int reset_iterate(Handle* h) {
+    const size_t S = h->ws.S, es = h->ops->elem_size;
+    auto zero = [&](int arr, int next) -> cudaError_t {
+        return cudaMemsetAsync((char*)h->ws.base + (size_t)h->ws.off[arr] * S * es, 0, (size_t)(h->ws.off[next] - h->ws.off[arr]) * S * es, h->stream);
+    };
+    CK(zero(A_V, A_Z));
+    CK(zero(A_LAM, A_TT));
+    CK(zero(A_PI, A_DPI));
+    CK(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * h->batch, h->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bnmpc_version(void) { return BNMPC_VERSION; }
+const char* bnmpc_last_error(void) { return g_err.c_str(); }
+
+int bnmpc_config_default(int model, bnmpc_config* c) {
+    if (!c) return fail(BNMPC_E_ARG, "cfg is NULL");
+    if (model < 0 || model > BNMPC_MODEL_JERK_DENSE) return fail(BNMPC_E_ARG, "unknown model");
+    memset(c, 0, sizeof(*c));
+    const bool jerk = (model == BNMPC_MODEL_JERK || model == BNMPC_MODEL_JERK_DENSE);
+    // reference src/params.py:37-61,113-122
+    const double MASS = 0.03277, G = 9.81, GR = G * MASS;
+    c->model = model; c->horizon = 30; c->precision = BNMPC_FP64; c->sqp_max_iter = 100; c->qp_max_iter = 50; c->rti = 0;
+    c->dt = 1.0 / 50;
+    for (int i = 0; i < 4; i++) { c->tol[i] = 1e-6; c->qp_tol[i] = 1e-6; }
+    c->mu0 = 1.0; c->thr0 = 0.1; c->alpha_min = 1e-8; c->lam_min = 1e-16; c->t_min = 1e-16;
+    const double wx[4] = {1e2, 1e2, 1.0, 1.0};
+    for (int i = 0; i < 4; i++) { c->W[i] = wx[i]; c->W_e[i] = wx[i]; }
+    if (jerk) {
+        // src/jerk_model/ocp.py:27-79, 84-92, 97-104
+        c->erk_stages = 1;
+        c->W[4] = c->W[5] = 0.0; c->W[6] = c->W[7] = 1e-1;
+        const double lb[6] = {-1.2, -1.2, -1, -1, -5, -5 + G}, ub[6] = {1.2, 1.2, 1, 1, 5, 5 + G};
+        memcpy(c->lbx, lb, sizeof(lb)); memcpy(c->ubx, ub, sizeof(ub));
+        c->lbu[0] = c->lbu[1] = -5; c->ubu[0] = c->ubu[1] = 5;
+        c->sim_erk_stages = 1; c->sim_substeps = 10; c->sim_dt = 1.0 / 500;
+    } else {
+        // src/force_model/ocp.py:28-78, 83-93, 98-104
+        c->erk_stages = 4;
+        c->W[4] = c->W[5] = 1e-1;
+        const double lb[4] = {-1.2, -1.2, -1, -1}, ub[4] = {1.2, 1.2, 1, 1};
+        memcpy(c->lbx, lb, sizeof(lb)); memcpy(c->ubx, ub, sizeof(ub));
+        c->lbu[0] = c->lbu[1] = -0.2 * GR; c->ubu[0] = c->ubu[1] = 1.3 * GR;
+        c->sim_erk_stages = 4; c->sim_substeps = 1; c->sim_dt = c->dt;
+    }
+    return 0;
+}
+
+int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) {
+    if (!cfg || !handle) return fail(BNMPC_E_ARG, "NULL argument");
+    if (batch < 1) return fail(BNMPC_E_ARG, "batch must be >= 1");
+    if (cfg->horizon < 1 || cfg->horizon > 1024) return fail(BNMPC_E_ARG, "horizon out of range");
+    if (cfg->erk_stages < 1 || cfg->erk_stages > 4 || cfg->sim_erk_stages < 1 || cfg->sim_erk_stages > 4)
+        return fail(BNMPC_E_ARG, "erk stages must be 1..4");
+    if (cfg->precision != BNMPC_FP64 && cfg->precision != BNMPC_FP32) return fail(BNMPC_E_ARG, "unknown precision");
+    const ModelOps* ops = pick_ops(cfg->model, cfg->precision);
+    if (!ops) return fail(BNMPC_E_ARG, "unknown model");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(BNMPC_E_CUDA, "no CUDA device: libbnmpc has no CPU path");
+    if (device < 0 || device >= ndev) return fail(BNMPC_E_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    Handle* h = new Handle();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg; h->opts = make_opts(*cfg); h->ops = ops; h->batch = batch; h->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete h; return fail(BNMPC_E_CUDA, cudaGetErrorString(e)); }
+    h->own_stream = true;
+    h->ws.B = batch;
+    h->ws.S = ((size_t)batch * ops->nblk + 127) / 128 * 128;
+    h->rows = ops->layout(cfg->horizon, h->ws.off);
+    h->ws_bytes = (size_t)h->rows * h->ws.S * ops->elem_size;
+    h->Bp = ((size_t)batch + 31) / 32 * 32;
+    bool ok = cudaMalloc(&h->ws.base, h->ws_bytes) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->ints, sizeof(int32_t) * 4 * batch) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->xs, sizeof(double) * 11 * h->Bp) == cudaSuccess;
+    if (!ok) {
+        const std::string msg = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
+        bnmpc_destroy(h);
+        return fail(BNMPC_E_CUDA, msg);
+    }
+    h->acc = h->xs + 4 * h->Bp; h->cost = h->acc + 2 * h->Bp; h->abs_err = h->cost + h->Bp; h->p_plant = h->abs_err + h->Bp;
+    h->ws.status = h->ints; h->ws.sqp_iter = h->ints + batch; h->ws.qp_iter = h->ints + 2 * batch; h->ws.have_mult = h->ints + 3 * batch;
+    h->tpb = default_tpb(h);
+    CK(cudaMemsetAsync(h->ws.base, 0, h->ws_bytes, h->stream));
+    CK(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * batch, h->stream));
+    CK(cudaMemsetAsync(h->xs, 0, sizeof(double) * 11 * h->Bp, h->stream));
+    // nominal parameters p = (mass, g) for every instance (reference src/params.py:37,42)
+    double* pnom = nullptr;
+    const double pn[2] = {0.03277, 9.81};
+    { const double* d; int rc = stage_in(h, 0, pn, 2, 0, &d); if (rc) { bnmpc_destroy(h); return rc; } pnom = const_cast<double*>(d); }
+    CK(ops->field(h->ws, F_P, 0, cfg->horizon, pnom, 0, 1, h->stream)); h->launches++;
+    CK(cudaStreamSynchronize(h->stream));
+    *handle = h;
+    return 0;
+}
+
+int bnmpc_destroy(void* handle) {
+    Handle* h = (Handle*)handle;
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->ws.base) cudaFree(h->ws.base);
+    if (h->ints) cudaFree(h->ints);
+    if (h->xs) cudaFree(h->xs);
+    for (int i = 0; i < 4; i++) if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int bnmpc_set_stream(void* handle, void* cuda_stream) {
+    Handle* h = (Handle*)handle;
+    if (!h) return fail(BNMPC_E_ARG, "NULL handle");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    CK(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { CK(cudaStreamDestroy(h->stream)); h->own_stream = false; }
+    h->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+int bnmpc_synchronize(void* handle) {
+    Handle* h = (Handle*)handle;
+    if (!h) return fail(BNMPC_E_ARG, "NULL handle");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int bnmpc_dims(void* handle, int32_t dims[7]) {
+    Handle* h = (Handle*)handle;
+    if (!h || !dims) return fail(BNMPC_E_ARG, "NULL argument");
+    dims[0] = h->ops->nx; dims[1] = h->ops->nu; dims[2] = h->ops->nx + h->ops->nu; dims[3] = h->ops->nx;
+    dims[4] = h->cfg.horizon; dims[5] = h->ops->np; dims[6] = h->ops->nblk;
+    return 0;
+}
+
+int64_t bnmpc_workspace_bytes(void* handle) {
+    Handle* h = (Handle*)handle;
+    return h ? (int64_t)(h->ws_bytes + sizeof(int32_t) * 4 * h->batch + sizeof(double) * 11 * h->Bp) : 0;
+}
+
+int bnmpc_set(void* handle, int stage, int field, const double* value, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !value) return fail(BNMPC_E_ARG, "NULL argument");
+    if (field < BNMPC_F_X || field > BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "unknown field");
+    if (field == BNMPC_F_PI || field == BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "field is read-only");
+    const int dim = h->ops->field_dim(field, stage, h->cfg.horizon);
+    if (dim <= 0) return fail(BNMPC_E_STAGE, "field does not exist at this stage");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const double* d;
+    if (int rc = stage_in(h, 0, value, (size_t)h->batch * dim, on_device, &d)) return rc;
+    CK(h->ops->field(h->ws, field, stage, h->cfg.horizon, const_cast<double*>(d), dim, 1, h->stream)); h->launches++;
+    return 0;
+}
+
+int bnmpc_get(void* handle, int stage, int field, double* out, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !out) return fail(BNMPC_E_ARG, "NULL argument");
+    if (field < BNMPC_F_X || field > BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "unknown field");
+    const int dim = h->ops->field_dim(field, stage, h->cfg.horizon);
+    if (dim <= 0) return fail(BNMPC_E_STAGE, "field does not exist at this stage");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    double* d;
+    if (int rc = stage_out_begin(h, 1, out, (size_t)h->batch * dim, on_device, &d)) return rc;
+    CK(h->ops->field(h->ws, field, stage, h->cfg.horizon, d, dim, 0, h->stream)); h->launches++;
+    return stage_out_end(h, 1, out, (size_t)h->batch * dim, on_device);
+}
+
+int bnmpc_set_yref_all(void* handle, const double* value, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !value) return fail(BNMPC_E_ARG, "NULL argument");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const int N = h->cfg.horizon;
+    const size_t per = (size_t)N * (h->ops->nx + h->ops->nu) + h->ops->nx;
+    const double* d;
+    if (int rc = stage_in(h, 2, value, per * h->batch, on_device, &d)) return rc;
+    CK(h->ops->yref_all(h->ws, N, d, h->stream)); h->launches++;
+    return 0;
+}
+
+int bnmpc_reset(void* handle) {
+    Handle* h = (Handle*)handle;
+    if (!h) return fail(BNMPC_E_ARG, "NULL handle");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    return reset_iterate(h);
+}
+
+int bnmpc_solve(void* handle) {
+    Handle* h = (Handle*)handle;
+    if (!h) return fail(BNMPC_E_ARG, "NULL handle");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    CK(h->ops->solve(h->ws, h->opts, h->tpb, h->stream)); h->launches++;
+    return 0;
+}
+
+int bnmpc_get_stats(void* handle, int which, int32_t* out, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !out) return fail(BNMPC_E_ARG, "NULL argument");
+    if (which < BNMPC_STAT_STATUS || which > BNMPC_STAT_QP_ITER) return fail(BNMPC_E_FIELD, "unknown statistic");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const int32_t* src = h->ints + (size_t)which * h->batch;
+    CK(cudaMemcpyAsync(out, src, sizeof(int32_t) * h->batch, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    if (!on_device) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int bnmpc_sim_step(void* handle, int substeps, const double* x, const double* u, const double* p_plant, const double* eps,
+                   double* x_next, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !x || !u || !x_next) return fail(BNMPC_E_ARG, "NULL argument");
+    if (substeps < 1) return fail(BNMPC_E_ARG, "substeps must be >= 1");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const int B = h->batch, nsub = substeps;
+    // one staging buffer: x | u | p | eps, and a second one for the result
+    const size_t nx_ = (size_t)B * 4, nu_ = (size_t)B * nsub * 2, np_ = p_plant ? (size_t)B * 2 : 0, ne_ = eps ? (size_t)B : 0;
+    const double *dx = x, *du = u, *dp = p_plant, *de = eps;
+    if (!on_device) {
+        std::vector<double> pack(nx_ + nu_ + np_ + ne_);
+        memcpy(pack.data(), x, nx_ * 8); memcpy(pack.data() + nx_, u, nu_ * 8);
+        if (p_plant) memcpy(pack.data() + nx_ + nu_, p_plant, np_ * 8);
+        if (eps) memcpy(pack.data() + nx_ + nu_ + np_, eps, ne_ * 8);
+        const double* d;
+        if (int rc = stage_in(h, 3, pack.data(), pack.size(), 0, &d)) return rc;
+        CK(cudaStreamSynchronize(h->stream));   // pack is a temporary
+        dx = d; du = d + nx_; dp = p_plant ? d + nx_ + nu_ : nullptr; de = eps ? d + nx_ + nu_ + np_ : nullptr;
+    }
+    double* dout;
+    if (int rc = stage_out_begin(h, 1, x_next, nx_, on_device, &dout)) return rc;
+    k_sim_step<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.sim_erk_stages, nsub, h->cfg.sim_dt, dx, du, dp, de, dout);
+    CK(cudaGetLastError()); h->launches++;
+    return stage_out_end(h, 1, x_next, nx_, on_device);
+}
+
+int bnmpc_closed_loop_init(void* handle, const double* x0, const double* p_ctrl, const double* p_plant) {
+    Handle* h = (Handle*)handle;
+    if (!h || !x0) return fail(BNMPC_E_ARG, "NULL argument");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    if (int rc = reset_iterate(h)) return rc;
+    const int B = h->batch;
+    k_loop_init<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->Bp, x0, p_ctrl, p_plant, h->xs, h->acc, h->cost, h->abs_err, h->p_plant);
+    CK(cudaGetLastError()); h->launches++;
+    if (p_ctrl) { CK(h->ops->par_from_bm(h->ws, p_ctrl, h->stream)); h->launches++; }
+    else {
+        const double pn[2] = {0.03277, 9.81};
+        const double* d;
+        if (int rc = stage_in(h, 0, pn, 2, 0, &d)) return rc;
+        CK(h->ops->field(h->ws, F_P, 0, h->cfg.horizon, const_cast<double*>(d), 0, 1, h->stream)); h->launches++;
+    }
+    return 0;
+}
+
+int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
+    Handle* h = (Handle*)handle;
+    if (!h || !a || !a->ref) return fail(BNMPC_E_ARG, "NULL argument");
+    if (a->n_steps < 0 || a->first_step < 0) return fail(BNMPC_E_ARG, "negative step count");
+    if (a->first_step + a->n_steps + h->cfg.horizon > a->ref_rows) return fail(BNMPC_E_ARG, "ref has too few rows for first_step + n_steps + N");
+    const bool logs = a->noise || a->Xsim || a->U_plant || a->U_ctrl || a->a_log || a->status || a->qp_iter;
+    if (logs && a->log_stride < a->first_step + a->n_steps) return fail(BNMPC_E_ARG, "log_stride too small");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    LoopArgs la;
+    memset(&la, 0, sizeof(la));
+    la.kind = h->ops->kind; la.ref_shared = a->ref_shared; la.log_stride = a->log_stride; la.batch = h->batch; la.Bp = h->Bp;
+    la.ref = a->ref; la.noise = a->noise; la.Xsim = a->Xsim; la.U_plant = a->U_plant; la.U_ctrl = a->U_ctrl; la.a_log = a->a_log;
+    la.status = a->status; la.qp_iter = a->qp_iter;
+    la.xs = h->xs; la.acc = h->acc; la.cost = h->cost; la.abs_err = h->abs_err; la.p_plant = h->p_plant;
+    for (int s = 0; s < a->n_steps; s++) {
+        la.step = a->first_step + s;
+        CK(h->ops->loop_step(h->ws, h->opts, la, h->tpb, h->stream)); h->launches++;
+    }
+    return 0;
+}
+
+int bnmpc_closed_loop_state(void* handle, double* cost, double* abs_err, double* x, double* acc) {
+    Handle* h = (Handle*)handle;
+    if (!h) return fail(BNMPC_E_ARG, "NULL handle");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const int B = h->batch;
+    k_loop_state<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->Bp, h->xs, h->acc, h->cost, h->abs_err, cost, abs_err, x, acc);
+    CK(cudaGetLastError()); h->launches++;
+    return 0;
+}
+
+int bnmpc_measure_fma_peak(int device, int precision, double* tflops) {
+    if (!tflops) return fail(BNMPC_E_ARG, "NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(BNMPC_E_CUDA, "no CUDA device: libbnmpc has no CPU path");
+    if (device < 0 || device >= ndev) return fail(BNMPC_E_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    return precision == BNMPC_FP32 ? fma_peak<float>(tflops) : fma_peak<double>(tflops);
+}
+
+int64_t bnmpc_launch_count(void* handle) {
+    Handle* h = (Handle*)handle;
+    return h ? h->launches : 0;
+}
+
+}  // extern "C"

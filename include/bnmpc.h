@@ -120,10 +120,12 @@ int bnmpc_solve(void* handle);
 /* ocp_solver.get_stats / status: int32 [batch] */
 int bnmpc_get_stats(void* handle, int which, int32_t* out, int on_device);
 
-/* OCP.simulate_next_x without the noise draw (src/force_model/ocp.py:106-112, src/jerk_model/ocp.py:106-113):
- * x AoS [batch][4], u AoS [batch][sim_substeps][2] = (theta, Fd) per sub-step, p_plant AoS [batch][2] or NULL
- * (nominal), eps [batch] or NULL added to all states of an instance (the np.random.normal draw, :114-115). */
-int bnmpc_sim_step(void* handle, const double* x, const double* u, const double* p_plant, const double* eps,
+/* AcadosSimSolver set('x')/set('u')/solve()/get('x') of the plant (src/force_model/ocp.py:106-112), `substeps` times
+ * in a row as OCP.simulate_next_x of the jerk path does (src/jerk_model/ocp.py:106-113): each sub-step is one ERK step
+ * (sim_erk_stages stages) of length sim_dt with its own input.
+ * x AoS [batch][4], u AoS [batch][substeps][2] = (theta, Fd) per sub-step, p_plant AoS [batch][2] or NULL (nominal),
+ * eps [batch] or NULL added to all states of an instance at the end (the np.random.normal draw, :114-115). */
+int bnmpc_sim_step(void* handle, int substeps, const double* x, const double* u, const double* p_plant, const double* eps,
                    double* x_next, int on_device);
 
 /* Fused closed loop = follow_trajectory (src/force_model/controller.py:8-56, src/jerk_model/controller.py:8-58) for
@@ -154,6 +156,11 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* args);
  * coordinates = calc_aed numerator, src/store_results.py:233-236), x [4][batch] current plant state, acc [2][batch]
  * (jerk a_i).  Any pointer may be NULL.  Device pointers. */
 int bnmpc_closed_loop_state(void* handle, double* cost, double* abs_err, double* x, double* acc);
+
+/* Measured FMA throughput of `device` in TFLOP/s for BNMPC_FP64 / BNMPC_FP32 (saturating kernel, 8 independent chains
+ * per thread, best of 5): the denominator of the roofline fraction bench.py reports (MEASURED_PEAKS.json has no
+ * vector-pipe figure). */
+int bnmpc_measure_fma_peak(int device, int precision, double* tflops);
 
 /* number of kernels this library has launched on the handle since creation */
 int64_t bnmpc_launch_count(void* handle);

@@ -1,0 +1,184 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI (ctypes shim), against
+the CPU oracle on the same seeded inputs and against the golden series decoded from the reference's own run.
+
+Tolerances: FP64 results within 1e-9 absolute of the oracle (well inside the north-star's 1e-6 relative on u0);
+status codes and SQP/QP iteration counts bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import drone_attitude_control_b200 as pkg
+from common import P_NOM, random_loop_inputs, random_solve_inputs
+from oracle import c_oracle as co
+from oracle import nmpc_oracle as o
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+X0_MAIN = np.array([1.0, 0.0, 0.0, 0.62])         # reference src/main.py:45
+MODEL_ID = {'force': 0, 'jerk': 1, 'force_dense': 0, 'jerk_dense': 1}
+
+
+def _gold_err(series, g, name):
+    st, v = g[name + '_step'], g[name]
+    m = st < len(series)
+    return float(np.max(np.abs(series[st[m]] - v[m])))
+
+
+def _run_loop(model, refs, x0, noise, pc, pp, S, **kw):
+    loop = pkg.BatchedClosedLoop(model, batch=x0.shape[0], device=0, **kw)
+    ref_t = torch.tensor(refs if refs.ndim == 2 else np.ascontiguousarray(np.transpose(refs, (1, 2, 0))))
+    loop.init(torch.tensor(x0.T.copy()), ref_t, noise=None if noise is None else torch.tensor(noise),
+              p_ctrl=torch.tensor(pc.T.copy()), p_plant=torch.tensor(pp.T.copy()), n_steps=S).run()
+    r = {k: v.cpu().numpy() for k, v in loop.results().items()}
+    return r, loop
+
+
+@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense', 'jerk_dense'])
+def test_single_solves_match_oracle(model):
+    B = 96
+    om = MODEL_ID[model]
+    oo = co.default_opts(om)
+    x0, yref = random_solve_inputs(om, B, seed=21 + om, spread=0.1)
+    want = co.solve_batch(oo, x0, yref, np.repeat(P_NOM[None], B, 0))
+    s = pkg.BatchedAcadosOcpSolver(model, batch=B, device=0)
+    s.set_yref_all(torch.tensor(yref, device='cuda'))
+    s.set(0, 'lbx', torch.tensor(x0, device='cuda'))
+    s.set(0, 'ubx', torch.tensor(x0, device='cuda'))
+    st = s.solve()
+    assert np.array_equal(st.cpu().numpy(), want['status'])
+    assert np.array_equal(s.get_stats('sqp_iter').cpu().numpy(), want['sqp_iter'])
+    assert np.array_equal(s.get_stats('qp_iter').cpu().numpy(), want['qp_iter'])
+    assert want['qp_iter'].max() > want['qp_iter'].min()          # the batch mixes easy and active-bound instances
+    for k in range(s.N):
+        np.testing.assert_allclose(s.get(k, 'u').cpu().numpy(), want['u'][:, k], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(s.get(k, 'pi').cpu().numpy(), want['pi'][:, k], rtol=0, atol=1e-8)
+    for k in range(s.N + 1):
+        np.testing.assert_allclose(s.get(k, 'x').cpu().numpy(), want['x'][:, k], rtol=0, atol=1e-9)
+    u0 = s.get(0, 'u').cpu().numpy()
+    rel = np.abs(u0 - want['u'][:, 0]) / np.maximum(np.abs(want['u'][:, 0]), 1e-3)
+    assert rel.max() < 1e-6                                        # the north-star's bound, with a wide margin
+
+
+@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense', 'jerk_dense'])
+def test_closed_loop_matches_oracle(model):
+    B, S = 48, 40
+    om = MODEL_ID[model]
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=5 + om, mass_sigma=0.05)
+    want = co.closed_loop(co.default_opts(om), refs, x0, noise, pc, pp, S)
+    got, loop = _run_loop(model, refs, x0, noise, pc, pp, S)
+    assert np.array_equal(got['status'], want['status'])
+    assert np.array_equal(got['qp_iter'], want['qp_iter'])
+    for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
+        np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-9, err_msg=k)
+    np.testing.assert_allclose(got['cost'], want['cost'], rtol=1e-10)
+    aed = np.mean(np.abs(refs[:, :S, :2] - want['Xsim'][:, :S, :2]), axis=(1, 2))
+    np.testing.assert_allclose(got['aed'], aed, rtol=1e-10)
+    assert loop.solver.launch_count() >= S
+
+
+@pytest.mark.parametrize('model,lo', [('force', 0), ('jerk', 500)])
+def test_fused_loop_reproduces_reference_run(model, lo):
+    """main.py as committed (seed 42, noise on): the decoded acados series, all 500 steps, B = 1 through the fused loop."""
+    g = np.load(os.path.join(GOLD, f'acados_{model}.npz'))
+    eps = o.main_py_noise()[lo:lo + 500]
+    got, _ = _run_loop(model, o.gen_circle_traj(), X0_MAIN[None], eps[:, None], P_NOM[None], P_NOM[None], 500)
+    assert np.all(got['status'] == 0)
+    assert _gold_err(got['U_plant'][0, :, 0], g, 'theta') < 5e-7
+    assert _gold_err(got['U_plant'][0, :, 1], g, 'Fd') < 1e-7
+    for name, col in (('px', 0), ('pz', 1), ('vx', 2), ('vz', 3)):
+        assert _gold_err(got['Xsim'][0, :, col], g, name) < 1e-7
+    if model == 'jerk':
+        assert _gold_err(got['a'][0, :, 0], g, 'ax') < 1e-6 and _gold_err(got['a'][0, :, 1], g, 'az') < 1e-6
+        assert float(got['cost'][0]) == pytest.approx(456.636, abs=1e-2)
+    else:
+        assert float(got['cost'][0]) == pytest.approx(66.3063, abs=1e-3)
+        assert float(got['aed'][0]) == pytest.approx(0.016563, abs=1e-5)
+
+
+def test_reference_style_main_reproduces_reference_run():
+    """The reference's own driver shape: np.random.seed(42); main(x0) -> force then jerk follow_trajectory through the
+    AcadosOcpSolver/AcadosSimSolver-style shims (set/solve/get per step, B = 1, numpy in/out)."""
+    from drone_attitude_control_b200.main import main
+    np.random.seed(42)
+    out = main(X0_MAIN.copy(), verbose=False)
+    for model in ('force', 'jerk'):
+        g = np.load(os.path.join(GOLD, f'acados_{model}.npz'))
+        r = out[model]
+        assert _gold_err(r['U_opt_plant'][:, 0], g, 'theta') < 5e-7
+        assert _gold_err(r['U_opt_plant'][:, 1], g, 'Fd') < 1e-7
+        assert _gold_err(r['Xsim'][:, 0], g, 'px') < 1e-7 and _gold_err(r['Xsim'][:, 1], g, 'pz') < 1e-7
+    assert out['force']['cost'] == pytest.approx(66.3063, abs=1e-3)
+    assert out['jerk']['cost'] == pytest.approx(456.636, abs=1e-2)
+
+
+def test_sharding_is_bit_invariant():
+    """Rank r of G owns a contiguous slice of instances; results must not depend on G (no collective on the path)."""
+    B, S = 64, 15
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=9)
+    whole, _ = _run_loop('force', refs, x0, noise, pc, pp, S)
+    for G in (2, 4):
+        n = B // G
+        parts = [_run_loop('force', refs[r * n:(r + 1) * n], x0[r * n:(r + 1) * n], noise[:, r * n:(r + 1) * n],
+                           pc[r * n:(r + 1) * n], pp[r * n:(r + 1) * n], S)[0] for r in range(G)]
+        for k in ('Xsim', 'U_ctrl', 'cost', 'qp_iter', 'status'):
+            assert np.array_equal(np.concatenate([p_[k] for p_ in parts]), whole[k]), (G, k)
+
+
+def test_sim_solver_matches_oracle():
+    rng = np.random.default_rng(2)
+    B = 33
+    x = rng.normal(size=(B, 4)); u = np.stack([rng.uniform(-0.6, 0.6, B), rng.uniform(0.1, 0.45, B)], 1)
+    for T, ns in ((0.02, 4), (0.002, 1)):
+        sim = pkg.BatchedAcadosSimSolver(T=T, num_stages=ns, batch=B, device=0, numpy_io=True)
+        got = sim.simulate(x=x, u=u)
+        want = co.sim_batch(x, u[:, None, :], np.repeat(P_NOM[None], B, 0), ns, 1, T)
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-14)
+
+
+def test_edge_cases_and_error_conventions():
+    s = pkg.BatchedAcadosOcpSolver('force', batch=3, device=0)
+    with pytest.raises(ValueError):
+        s.set(0, 'nope', np.zeros((3, 4)))
+    with pytest.raises(ValueError):
+        s.set(5, 'lbx', np.zeros((3, 4)))           # x0 embedding exists at stage 0 only
+    with pytest.raises(ValueError):
+        s.set(0, 'yref', np.zeros((3, 5)))          # wrong dimension
+    with pytest.raises(pkg.BnmpcError):
+        pkg._lib.check(pkg.lib().bnmpc_set(s.handle, 0, 6, None, 0))      # NULL pointer / read-only field
+    # NaN in x0 -> acados status 1 (ACADOS_FAILURE) for that instance only; the others solve normally
+    x0, yref = random_solve_inputs(0, 3, seed=1)
+    x0[1, 2] = np.nan
+    s.set_yref_all(yref); s.set(0, 'lbx', x0); s.set(0, 'ubx', x0)
+    st = s.solve().cpu().numpy()
+    assert st.tolist() == [0, 1, 0]
+    # an instance whose start state violates the (hard) state bounds far enough is infeasible: QP reaches its iteration
+    # cap and acados reports status 2 / 4 instead of hanging (hard part 3)
+    x0, yref = random_solve_inputs(0, 3, seed=1)
+    x0[2] = [3.0, 3.0, 0.0, 0.0]
+    s.reset(); s.set_yref_all(yref); s.set(0, 'lbx', x0); s.set(0, 'ubx', x0)
+    st = s.solve().cpu().numpy()
+    want = co.solve_batch(co.default_opts(0), x0, yref, np.repeat(P_NOM[None], 3, 0))
+    assert st.tolist() == want['status'].tolist() and st[2] != 0
+    assert s.get_stats('qp_iter').cpu().numpy().tolist() == want['qp_iter'].tolist()
+
+
+def test_horizon_and_rti_variants():
+    """Horizon sweep sizes of BASELINE config 5 (N = 20 / 50 / 100) and the north-star's SQP_RTI mode."""
+    B = 8
+    for N in (20, 50, 100):
+        x0, yref = random_solve_inputs(0, B, seed=N, N=N)
+        want = co.solve_batch(co.default_opts(0, N=N), x0, yref, np.repeat(P_NOM[None], B, 0))
+        s = pkg.BatchedAcadosOcpSolver('force', batch=B, device=0, N_horizon=N)
+        s.set_yref_all(yref); s.set(0, 'lbx', x0); s.set(0, 'ubx', x0)
+        assert np.array_equal(s.solve().cpu().numpy(), want['status'])
+        assert np.array_equal(s.get_stats('qp_iter').cpu().numpy(), want['qp_iter'])
+        np.testing.assert_allclose(s.get(0, 'u').cpu().numpy(), want['u'][:, 0], rtol=0, atol=1e-9)
+    x0, yref = random_solve_inputs(1, B, seed=77)
+    want = co.solve_batch(co.default_opts(1, rti=True), x0, yref, np.repeat(P_NOM[None], B, 0))
+    s = pkg.BatchedAcadosOcpSolver('jerk', batch=B, device=0, rti=True)
+    s.set_yref_all(yref); s.set(0, 'lbx', x0); s.set(0, 'ubx', x0)
+    assert np.array_equal(s.solve().cpu().numpy(), want['status'])
+    assert np.array_equal(s.get_stats('sqp_iter').cpu().numpy(), want['sqp_iter'])
+    np.testing.assert_allclose(s.get(0, 'u').cpu().numpy(), want['u'][:, 0], rtol=0, atol=1e-9)

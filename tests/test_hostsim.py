@@ -1,0 +1,37 @@
+"""CPU-only check of the PRODUCT's solver templates (csrc/bnmpc_core.cuh, bnmpc_loop.cuh compiled for the host by
+tests/hostsim, a test harness that is not part of the library) against the C oracle.  The GPU parity tests
+(test_gpu_parity.py) repeat this through the C-ABI on the device."""
+import numpy as np
+import pytest
+
+import hostsim as hs
+from common import random_loop_inputs, random_solve_inputs
+from oracle import c_oracle as co
+
+
+@pytest.mark.parametrize('model', [0, 1, 2, 3])
+def test_single_solves_match_oracle(model):
+    om = model % 2
+    oo = co.default_opts(om)
+    x0, yref = random_solve_inputs(om, 5, seed=11 + model)
+    p = np.repeat(np.array([[0.03277, 9.81]]), 5, 0)
+    want = co.solve_batch(oo, x0, yref, p)
+    got = hs.solve_batch(model, hs.FP64, hs.opts_from_oracle(oo), x0, yref, p)
+    assert np.array_equal(got['status'], want['status'])
+    assert np.array_equal(got['sqp_iter'], want['sqp_iter']) and np.array_equal(got['qp_iter'], want['qp_iter'])
+    np.testing.assert_allclose(got['u'], want['u'], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got['x'], want['x'], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got['pi'], want['pi'], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize('model', [0, 1])
+def test_closed_loop_matches_oracle(model):
+    S, B = 25, 3
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=3 + model, mass_sigma=0.05)
+    oo = co.default_opts(model)
+    want = co.closed_loop(oo, refs, x0, noise, pc, pp, S)
+    got = hs.closed_loop(model, hs.FP64, hs.opts_from_oracle(oo), refs, x0, noise, pc, pp, S)
+    assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
+    for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
+        np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-10, err_msg=k)
+    np.testing.assert_allclose(got['cost'], want['cost'], rtol=1e-12)
