@@ -46,7 +46,8 @@ class BatchedClosedLoop:
             assert tuple(self.ref.shape[1:]) == (8, B)
         self.n_steps = int(n_steps if n_steps is not None else self.ref.shape[0] - self.N)
         assert self.ref.shape[0] >= self.n_steps + self.N
-        self.noise = self._dev(noise, (self.n_steps, B)) if noise is not None else None
+        self.noise = self._dev(noise)[:self.n_steps].contiguous() if noise is not None else None
+        assert self.noise is None or tuple(self.noise.shape) == (self.n_steps, B)
         self.p_ctrl = self._dev(p_ctrl, (2, B)) if p_ctrl is not None else None
         self.p_plant = self._dev(p_plant, (2, B)) if p_plant is not None else None
         ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
