@@ -27,12 +27,12 @@ struct Handle {
     bnmpc_config cfg;
     Opts opts;
     const ModelOps* ops;
-    int batch, device, tpb;
+    int batch, device, wpc;        // wpc: warps (= instances) per CTA
     cudaStream_t stream;
     bool own_stream;
-    WsAny ws;
-    int rows;
-    size_t ws_bytes;
+    GsAny gs;                      // persistent per-instance state in HBM
+    char* gs_base;
+    size_t gs_bytes, nV, nPI, nLAM;   // elements per instance
     int32_t* ints;                 // status | sqp_iter | qp_iter | have_mult
     double* stage[4];              // device staging buffers for host<->device AoS copies
     size_t stage_cap[4];
@@ -101,6 +101,50 @@ int stage_out_end(Handle* h, int slot, double* p, size_t count, int on_device) {
     CK(cudaMemcpyAsync(p, h->stage[slot], count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return 0;
+}
+
+// ocp_solver.set / get for all instances: AoS [B][dim] (FP64) <-> persistent state
+template <class T, bool TO_STATE>
+__global__ void k_field(const __grid_constant__ Gs<T> gs, int NX, int NU, int NP, int field, int stage, double* aos, int dim, int aos_stride) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = (int)(idx / dim), j = (int)(idx % dim);
+    if (inst >= gs.B) return;
+    T* p = field_ptr(gs, NX, NU, NP, inst, field, stage, j);
+    if (TO_STATE) *p = T(aos[(size_t)inst * aos_stride + j]); else aos[(size_t)inst * aos_stride + j] = double(*p);
+}
+
+// OCP.set_up_ocp in one call: [B][N*ny + ny_e]
+template <class T>
+__global__ void k_yref_all(const __grid_constant__ Gs<T> gs, int NX, int NU, int NP, const double* aos) {
+    const int ny = NX + NU, per = gs.N * ny + NX;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int inst = (int)(idx / per), e = (int)(idx % per);
+    if (inst >= gs.B) return;
+    const int k = e < gs.N * ny ? e / ny : gs.N, j = e - k * ny;
+    *field_ptr(gs, NX, NU, NP, inst, F_YREF, k, j) = T(aos[idx]);
+}
+
+// p_ctrl [NP][B] batch-minor -> parameters
+template <class T>
+__global__ void k_par_from_bm(const __grid_constant__ Gs<T> gs, int NP, const double* p_ctrl) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= gs.B) return;
+    for (int j = 0; j < NP; j++) gs.PAR[(size_t)i * NP + j] = T(p_ctrl[(size_t)j * gs.B + i]);
+}
+
+template <class T>
+cudaError_t launch_field(Handle* h, int field, int stage, double* aos, int dim, int stride, int to_state) {
+    const size_t tot = (size_t)h->batch * dim;
+    const int grid = (int)((tot + 127) / 128);
+    const Gs<T> g = gs_cast<T>(h->gs);
+    if (to_state) k_field<T, true><<<grid, 128, 0, h->stream>>>(g, h->ops->nx, h->ops->nu, h->ops->np, field, stage, aos, dim, stride);
+    else k_field<T, false><<<grid, 128, 0, h->stream>>>(g, h->ops->nx, h->ops->nu, h->ops->np, field, stage, aos, dim, stride);
+    h->launches++;
+    return cudaGetLastError();
+}
+cudaError_t field_xfer(Handle* h, int field, int stage, double* aos, int dim, int stride, int to_state) {
+    return h->ops->elem_size == 8 ? launch_field<double>(h, field, stage, aos, dim, stride, to_state)
+                                  : launch_field<float>(h, field, stage, aos, dim, stride, to_state);
 }
 
 __global__ void k_sim_step(int B, int ns, int nsub, double hstep, const double* x, const double* u, const double* p_plant,
@@ -188,23 +232,19 @@ int fma_peak(double* tflops) {
     return 0;
 }
 
-int default_tpb(const Handle* h) {
-    if (h->cfg.threads_per_block > 0) return (h->cfg.threads_per_block + 31) / 32 * 32;
-    // few instances: one warp per CTA spreads the warps over all SMs; many: larger CTAs
-    const size_t warps = h->ws.S / 32;
-    if (warps <= 148 * 8) return 32;
-    if (warps <= 148 * 32) return 64;
-    return 128;
+// warps (= instances) per CTA: one by default (the CTA is only a packing unit; small CTAs pack shared memory best)
+int default_wpc(const Handle* h) {
+    int w = h->cfg.threads_per_block > 0 ? (h->cfg.threads_per_block + 31) / 32 : 1;
+    const size_t per = h->ops->smem_bytes(h->cfg.horizon);
+    while (w > 1 && per * w > 227 * 1024) w--;
+    return w;
 }
 
 int reset_iterate(Handle* h) {
-    const size_t S = h->ws.S, es = h->ops->elem_size;
-    auto zero = [&](int arr, int next) -> cudaError_t {
-        return cudaMemsetAsync((char*)h->ws.base + (size_t)h->ws.off[arr] * S * es, 0, (size_t)(h->ws.off[next] - h->ws.off[arr]) * S * es, h->stream);
-    };
-    CK(zero(A_V, A_Z));
-    CK(zero(A_LAM, A_TT));
-    CK(zero(A_PI, A_DPI));
+    const size_t es = h->ops->elem_size, B = h->batch;
+    CK(cudaMemsetAsync(h->gs.V, 0, B * h->nV * es, h->stream));
+    CK(cudaMemsetAsync(h->gs.PI, 0, B * h->nPI * es, h->stream));
+    CK(cudaMemsetAsync(h->gs.LAM, 0, B * h->nLAM * es, h->stream));
     CK(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * h->batch, h->stream));
     return 0;
 }
@@ -269,12 +309,13 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(BNMPC_E_CUDA, cudaGetErrorString(e)); }
     h->own_stream = true;
-    h->ws.B = batch;
-    h->ws.S = ((size_t)batch * ops->nblk + 127) / 128 * 128;
-    h->rows = ops->layout(cfg->horizon, h->ws.off);
-    h->ws_bytes = (size_t)h->rows * h->ws.S * ops->elem_size;
+    if (ops->smem_bytes(cfg->horizon) > 227 * 1024) { delete h; return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of one instance exceeds 227 KB of shared memory"); }
+    const size_t SGd = ops->nu + ops->nx, Nn = cfg->horizon, es = ops->elem_size;
+    h->nV = (Nn + 1) * SGd; h->nPI = Nn * ops->nx; h->nLAM = Nn * 2 * SGd;
+    const size_t per = 2 * h->nV + h->nPI + h->nLAM + ops->nx + ops->np;
+    h->gs_bytes = per * batch * es;
     h->Bp = ((size_t)batch + 31) / 32 * 32;
-    bool ok = cudaMalloc(&h->ws.base, h->ws_bytes) == cudaSuccess;
+    bool ok = cudaMalloc(&h->gs_base, h->gs_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&h->ints, sizeof(int32_t) * 4 * batch) == cudaSuccess;
     ok = ok && cudaMalloc(&h->xs, sizeof(double) * 11 * h->Bp) == cudaSuccess;
     if (!ok) {
@@ -283,16 +324,22 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
         return fail(BNMPC_E_CUDA, msg);
     }
     h->acc = h->xs + 4 * h->Bp; h->cost = h->acc + 2 * h->Bp; h->abs_err = h->cost + h->Bp; h->p_plant = h->abs_err + h->Bp;
-    h->ws.status = h->ints; h->ws.sqp_iter = h->ints + batch; h->ws.qp_iter = h->ints + 2 * batch; h->ws.have_mult = h->ints + 3 * batch;
-    h->tpb = default_tpb(h);
-    CK(cudaMemsetAsync(h->ws.base, 0, h->ws_bytes, h->stream));
+    {
+        char* p = h->gs_base;
+        h->gs.V = p; p += h->nV * batch * es; h->gs.PI = p; p += h->nPI * batch * es; h->gs.LAM = p; p += h->nLAM * batch * es;
+        h->gs.YREF = p; p += h->nV * batch * es; h->gs.X0 = p; p += (size_t)ops->nx * batch * es; h->gs.PAR = p;
+    }
+    h->gs.status = h->ints; h->gs.sqp_iter = h->ints + batch; h->gs.qp_iter = h->ints + 2 * batch; h->gs.have_mult = h->ints + 3 * batch;
+    h->gs.B = batch; h->gs.N = cfg->horizon;
+    h->wpc = default_wpc(h);
+    CK(cudaMemsetAsync(h->gs_base, 0, h->gs_bytes, h->stream));
     CK(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * batch, h->stream));
     CK(cudaMemsetAsync(h->xs, 0, sizeof(double) * 11 * h->Bp, h->stream));
     // nominal parameters p = (mass, g) for every instance (reference src/params.py:37,42)
     double* pnom = nullptr;
     const double pn[2] = {0.03277, 9.81};
     { const double* d; int rc = stage_in(h, 0, pn, 2, 0, &d); if (rc) { bnmpc_destroy(h); return rc; } pnom = const_cast<double*>(d); }
-    CK(ops->field(h->ws, F_P, 0, cfg->horizon, pnom, 0, 1, h->stream)); h->launches++;
+    CK(field_xfer(h, F_P, 0, pnom, ops->np, 0, 1));
     CK(cudaStreamSynchronize(h->stream));
     *handle = h;
     return 0;
@@ -303,7 +350,7 @@ int bnmpc_destroy(void* handle) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->ws.base) cudaFree(h->ws.base);
+    if (h->gs_base) cudaFree(h->gs_base);
     if (h->ints) cudaFree(h->ints);
     if (h->xs) cudaFree(h->xs);
     for (int i = 0; i < 4; i++) if (h->stage[i]) cudaFree(h->stage[i]);
@@ -340,7 +387,7 @@ int bnmpc_dims(void* handle, int32_t dims[7]) {
 
 int64_t bnmpc_workspace_bytes(void* handle) {
     Handle* h = (Handle*)handle;
-    return h ? (int64_t)(h->ws_bytes + sizeof(int32_t) * 4 * h->batch + sizeof(double) * 11 * h->Bp) : 0;
+    return h ? (int64_t)(h->gs_bytes + sizeof(int32_t) * 4 * h->batch + sizeof(double) * 11 * h->Bp) : 0;
 }
 
 int bnmpc_set(void* handle, int stage, int field, const double* value, int on_device) {
@@ -348,12 +395,12 @@ int bnmpc_set(void* handle, int stage, int field, const double* value, int on_de
     if (!h || !value) return fail(BNMPC_E_ARG, "NULL argument");
     if (field < BNMPC_F_X || field > BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "unknown field");
     if (field == BNMPC_F_PI || field == BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "field is read-only");
-    const int dim = h->ops->field_dim(field, stage, h->cfg.horizon);
+    const int dim = field_dim(h->ops->nx, h->ops->nu, h->ops->np, field, stage, h->cfg.horizon);
     if (dim <= 0) return fail(BNMPC_E_STAGE, "field does not exist at this stage");
     if (use_device(h)) return BNMPC_E_CUDA;
     const double* d;
     if (int rc = stage_in(h, 0, value, (size_t)h->batch * dim, on_device, &d)) return rc;
-    CK(h->ops->field(h->ws, field, stage, h->cfg.horizon, const_cast<double*>(d), dim, 1, h->stream)); h->launches++;
+    CK(field_xfer(h, field, stage, const_cast<double*>(d), dim, dim, 1));
     return 0;
 }
 
@@ -361,12 +408,12 @@ int bnmpc_get(void* handle, int stage, int field, double* out, int on_device) {
     Handle* h = (Handle*)handle;
     if (!h || !out) return fail(BNMPC_E_ARG, "NULL argument");
     if (field < BNMPC_F_X || field > BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "unknown field");
-    const int dim = h->ops->field_dim(field, stage, h->cfg.horizon);
+    const int dim = field_dim(h->ops->nx, h->ops->nu, h->ops->np, field, stage, h->cfg.horizon);
     if (dim <= 0) return fail(BNMPC_E_STAGE, "field does not exist at this stage");
     if (use_device(h)) return BNMPC_E_CUDA;
     double* d;
     if (int rc = stage_out_begin(h, 1, out, (size_t)h->batch * dim, on_device, &d)) return rc;
-    CK(h->ops->field(h->ws, field, stage, h->cfg.horizon, d, dim, 0, h->stream)); h->launches++;
+    CK(field_xfer(h, field, stage, d, dim, dim, 0));
     return stage_out_end(h, 1, out, (size_t)h->batch * dim, on_device);
 }
 
@@ -378,7 +425,13 @@ int bnmpc_set_yref_all(void* handle, const double* value, int on_device) {
     const size_t per = (size_t)N * (h->ops->nx + h->ops->nu) + h->ops->nx;
     const double* d;
     if (int rc = stage_in(h, 2, value, per * h->batch, on_device, &d)) return rc;
-    CK(h->ops->yref_all(h->ws, N, d, h->stream)); h->launches++;
+    {
+        const size_t tot = per * h->batch;
+        const int grid = (int)((tot + 127) / 128);
+        if (h->ops->elem_size == 8) k_yref_all<double><<<grid, 128, 0, h->stream>>>(gs_cast<double>(h->gs), h->ops->nx, h->ops->nu, h->ops->np, d);
+        else k_yref_all<float><<<grid, 128, 0, h->stream>>>(gs_cast<float>(h->gs), h->ops->nx, h->ops->nu, h->ops->np, d);
+        CK(cudaGetLastError()); h->launches++;
+    }
     return 0;
 }
 
@@ -393,7 +446,7 @@ int bnmpc_solve(void* handle) {
     Handle* h = (Handle*)handle;
     if (!h) return fail(BNMPC_E_ARG, "NULL handle");
     if (use_device(h)) return BNMPC_E_CUDA;
-    CK(h->ops->solve(h->ws, h->opts, h->tpb, h->stream)); h->launches++;
+    CK(h->ops->solve(h->gs, h->opts, h->wpc, h->stream)); h->launches++;
     return 0;
 }
 
@@ -443,12 +496,15 @@ int bnmpc_closed_loop_init(void* handle, const double* x0, const double* p_ctrl,
     const int B = h->batch;
     k_loop_init<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->Bp, x0, p_ctrl, p_plant, h->xs, h->acc, h->cost, h->abs_err, h->p_plant);
     CK(cudaGetLastError()); h->launches++;
-    if (p_ctrl) { CK(h->ops->par_from_bm(h->ws, p_ctrl, h->stream)); h->launches++; }
-    else {
+    if (p_ctrl) {
+        if (h->ops->elem_size == 8) k_par_from_bm<double><<<(B + 127) / 128, 128, 0, h->stream>>>(gs_cast<double>(h->gs), h->ops->np, p_ctrl);
+        else k_par_from_bm<float><<<(B + 127) / 128, 128, 0, h->stream>>>(gs_cast<float>(h->gs), h->ops->np, p_ctrl);
+        CK(cudaGetLastError()); h->launches++;
+    } else {
         const double pn[2] = {0.03277, 9.81};
         const double* d;
         if (int rc = stage_in(h, 0, pn, 2, 0, &d)) return rc;
-        CK(h->ops->field(h->ws, F_P, 0, h->cfg.horizon, const_cast<double*>(d), 0, 1, h->stream)); h->launches++;
+        CK(field_xfer(h, F_P, 0, const_cast<double*>(d), h->ops->np, 0, 1));
     }
     return 0;
 }
@@ -469,7 +525,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     la.xs = h->xs; la.acc = h->acc; la.cost = h->cost; la.abs_err = h->abs_err; la.p_plant = h->p_plant;
     for (int s = 0; s < a->n_steps; s++) {
         la.step = a->first_step + s;
-        CK(h->ops->loop_step(h->ws, h->opts, la, h->tpb, h->stream)); h->launches++;
+        CK(h->ops->loop_step(h->gs, h->opts, la, h->wpc, h->stream)); h->launches++;
     }
     return 0;
 }

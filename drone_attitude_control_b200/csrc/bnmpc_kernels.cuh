@@ -1,6 +1,9 @@
 // bnmpc_kernels.cuh - __global__ wrappers around the solver templates and the per-model launch table.
 // Each model_*.cu instantiates BNMPC_DEFINE_MODEL_OPS for one generated model (both precisions); bnmpc_api.cu only
 // sees the ModelOps table, so the heavy templates compile in parallel translation units.
+//
+// Launch shape: one warp per OCP instance, `wpc` warps per CTA, each warp with its own slice of dynamic shared memory
+// (SmLayout<M>::elems(N) elements).  There is no inter-warp synchronisation; the CTA is only a packing unit.
 #pragma once
 #include <cuda_runtime.h>
 #include <string.h>
@@ -9,101 +12,80 @@
 
 namespace bnmpc {
 
-// type-erased Ws<T> (identical layout for every T)
-struct WsAny {
-    void* base; size_t S; int B; int off[A_COUNT];
+// type-erased Gs<T> (identical layout for every T)
+struct GsAny {
+    void *V, *PI, *LAM, *YREF, *X0, *PAR;
     int32_t *status, *sqp_iter, *qp_iter, *have_mult;
+    int B, N;
 };
-template <class T> inline Ws<T> ws_cast(const WsAny& a) {
-    static_assert(sizeof(Ws<T>) == sizeof(WsAny), "layout");
-    Ws<T> w; memcpy(&w, &a, sizeof(w)); return w;
+template <class T> inline Gs<T> gs_cast(const GsAny& a) {
+    static_assert(sizeof(Gs<T>) == sizeof(GsAny), "layout");
+    Gs<T> g; memcpy(&g, &a, sizeof(g)); return g;
 }
 
 struct ModelOps {
     const char* name;
-    int nx, nu, np, nblk, nxb, nub, kind, jac_const, elem_size;
-    int (*layout)(int N, int* off);                                                     // rows of the workspace
-    int (*field_dim)(int field, int stage, int N);
-    cudaError_t (*solve)(const WsAny&, const Opts&, int tpb, cudaStream_t);
-    cudaError_t (*loop_step)(const WsAny&, const Opts&, const LoopArgs&, int tpb, cudaStream_t);
-    // AoS [B][dim] (stride `aos_stride` doubles between instances; 0 = one vector for all) <-> workspace
-    cudaError_t (*field)(const WsAny&, int field, int stage, int N, double* aos, int aos_stride, int to_ws, cudaStream_t);
-    cudaError_t (*yref_all)(const WsAny&, int N, const double* aos, cudaStream_t);
-    // p_ctrl [2][B] batch-minor -> workspace parameters
-    cudaError_t (*par_from_bm)(const WsAny&, const double* p_ctrl, cudaStream_t);
+    int nx, nu, np, nblk, nxb, nub, kind, jac_const, elem_size, sm_rows;
+    size_t (*smem_bytes)(int N);                                    // dynamic shared memory of one instance
+    cudaError_t (*solve)(const GsAny&, const Opts&, int wpc, cudaStream_t);
+    cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int wpc, cudaStream_t);
 };
 
 template <class M, class T>
-__global__ void k_solve(const __grid_constant__ Ws<T> w, const __grid_constant__ Opts o) {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int inst = (int)(slot / M::NBLK), b = (int)(slot % M::NBLK);
-    const WarpXchg<M::NBLK> xc;
-    BlockSolver<M, T, WarpXchg<M::NBLK>> bs(w, o, xc, slot, b);
-    bs.sqp_solve(inst < w.B, inst);
+__device__ __forceinline__ T* warp_smem(int N) {
+    extern __shared__ double4 smem_raw[];
+    const size_t per = (SmLayout<M>::elems(N) * sizeof(T) + 15) / 16 * 16;
+    return reinterpret_cast<T*>(reinterpret_cast<char*>(smem_raw) + per * (threadIdx.x >> 5));
 }
 
 template <class M, class T>
-__global__ void k_loop_step(const __grid_constant__ Ws<T> w, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a) {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int inst = (int)(slot / M::NBLK), b = (int)(slot % M::NBLK);
-    const WarpXchg<M::NBLK> xc;
-    BlockSolver<M, T, WarpXchg<M::NBLK>> bs(w, o, xc, slot, b);
-    closed_loop_step<M, T>(bs, inst < w.B, inst, a);
-}
-
-template <class M, class T, bool TO_WS>
-__global__ void k_field(const __grid_constant__ Ws<T> w, int field, int stage, int N, double* aos, int aos_stride) {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int inst = (int)(slot / M::NBLK), b = (int)(slot % M::NBLK);
-    if (inst >= w.B) return;
-    field_xfer<M, T, TO_WS>(w, slot, b, field, stage, N, aos + (size_t)inst * aos_stride);
+__global__ void k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o) {
+    const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (inst >= gs.B) return;          // whole warp
+    const WarpGroup<32> g;
+    Solver<M, T, WarpGroup<32>> sv(warp_smem<M, T>(o.N), o, g);
+    api_solve<M, T>(sv, inst, gs);
 }
 
 template <class M, class T>
-__global__ void k_yref_all(const __grid_constant__ Ws<T> w, int N, const double* aos) {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int inst = (int)(slot / M::NBLK), b = (int)(slot % M::NBLK);
-    if (inst >= w.B) return;
-    yref_all_to_ws<M, T>(w, slot, b, N, aos + (size_t)inst * (N * (M::NX + M::NU) + M::NX));
-}
-
-template <class M, class T>
-__global__ void k_par_from_bm(const __grid_constant__ Ws<T> w, const double* p_ctrl) {
-    const size_t slot = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int inst = (int)(slot / M::NBLK);
-    if (inst >= w.B) return;
-#pragma unroll
-    for (int j = 0; j < M::NP; j++) w.base[(size_t)(w.off[A_PAR] + j) * w.S + slot] = T(p_ctrl[(size_t)j * w.B + inst]);
+__global__ void k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a) {
+    const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (inst >= gs.B) return;          // whole warp
+    const WarpGroup<32> g;
+    Solver<M, T, WarpGroup<32>> sv(warp_smem<M, T>(o.N), o, g);
+    closed_loop_step<M, T>(sv, inst, gs, a);
 }
 
 template <class M, class T>
 struct OpsImpl {
-    static int grid(const WsAny& a, int tpb) { return (int)((a.S + tpb - 1) / tpb); }
-    static cudaError_t solve(const WsAny& a, const Opts& o, int tpb, cudaStream_t st) {
-        k_solve<M, T><<<grid(a, tpb), tpb, 0, st>>>(ws_cast<T>(a), o);
+    static size_t smem_bytes(int N) { return (SmLayout<M>::elems(N) * sizeof(T) + 15) / 16 * 16; }
+    template <class K>
+    static cudaError_t prep(K kern, size_t bytes) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    }
+    static cudaError_t solve(const GsAny& a, const Opts& o, int wpc, cudaStream_t st) {
+        const size_t bytes = smem_bytes(o.N) * wpc;
+        cudaError_t e = prep(k_solve<M, T>, bytes);
+        if (e != cudaSuccess) return e;
+        k_solve<M, T><<<(a.B + wpc - 1) / wpc, 32 * wpc, bytes, st>>>(gs_cast<T>(a), o);
         return cudaGetLastError();
     }
-    static cudaError_t loop_step(const WsAny& a, const Opts& o, const LoopArgs& la, int tpb, cudaStream_t st) {
-        k_loop_step<M, T><<<grid(a, tpb), tpb, 0, st>>>(ws_cast<T>(a), o, la);
+    static cudaError_t loop_step(const GsAny& a, const Opts& o, const LoopArgs& la, int wpc, cudaStream_t st) {
+        const size_t bytes = smem_bytes(o.N) * wpc;
+        static size_t prepared = 0;
+        if (prepared != bytes) {
+            cudaError_t e = prep(k_loop_step<M, T>, bytes);
+            if (e != cudaSuccess) return e;
+            prepared = bytes;
+        }
+        k_loop_step<M, T><<<(a.B + wpc - 1) / wpc, 32 * wpc, bytes, st>>>(gs_cast<T>(a), o, la);
         return cudaGetLastError();
     }
-    static cudaError_t field(const WsAny& a, int field, int stage, int N, double* aos, int stride, int to_ws, cudaStream_t st) {
-        if (to_ws) k_field<M, T, true><<<grid(a, 128), 128, 0, st>>>(ws_cast<T>(a), field, stage, N, aos, stride);
-        else k_field<M, T, false><<<grid(a, 128), 128, 0, st>>>(ws_cast<T>(a), field, stage, N, aos, stride);
-        return cudaGetLastError();
-    }
-    static cudaError_t yref_all(const WsAny& a, int N, const double* aos, cudaStream_t st) {
-        k_yref_all<M, T><<<grid(a, 128), 128, 0, st>>>(ws_cast<T>(a), N, aos);
-        return cudaGetLastError();
-    }
-    static cudaError_t par_from_bm(const WsAny& a, const double* p, cudaStream_t st) {
-        k_par_from_bm<M, T><<<grid(a, 128), 128, 0, st>>>(ws_cast<T>(a), p);
-        return cudaGetLastError();
-    }
-    static int fdim(int field, int stage, int N) { return field_dim<M>(field, stage, N); }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        &WsLayout<M>::fill, &fdim, &solve, &loop_step, &field, &yref_all, &par_from_bm};
+                        SmLayout<M>::ROWS, &smem_bytes, &solve, &loop_step};
     }
 };
 

@@ -1,94 +1,74 @@
 // hostsim - TEST HARNESS ONLY.  Compiles the solver arithmetic of the product (csrc/bnmpc_core.cuh, bnmpc_loop.cuh,
 // the same __host__ __device__ templates the CUDA kernels instantiate) for the host CPU so that the device code's logic
 // can be checked against the oracle in the CPU-only test run.  It is NOT part of libbnmpc.so and nothing in the
-// product package can reach it: the product has no CPU path.  The NBLK threads of an instance (warp lanes on the
-// GPU) are emulated by NBLK host threads that exchange the interior-point scalars through a barrier.
+// product package can reach it: the product has no CPU path.  The warp that owns an instance on the GPU is emulated
+// by a single "lane" (group size 1) that walks all (stage, block) items in order.
 #define __host__
 #define __device__
 #define __forceinline__ inline __attribute__((always_inline))
-#include <pthread.h>
+#define __noinline__ __attribute__((noinline))
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
-#include <thread>
 
 #include "../../drone_attitude_control_b200/csrc/bnmpc_loop.cuh"
 
 using namespace bnmpc;
 
-template <int NBLK>
-struct HostShared { pthread_barrier_t bar; double slot[NBLK]; };
-
-template <int NBLK>
-struct HostXchg {
-    HostShared<NBLK>* sh; int b;
-    template <class T> T exchange(T v, int mode, int src = 0) const {
-        if (NBLK == 1) return v;
-        sh->slot[b] = (double)v;
-        pthread_barrier_wait(&sh->bar);
-        double r = sh->slot[0];
-        if (mode == 0) { for (int i = 1; i < NBLK; i++) r = sh->slot[i] > r ? sh->slot[i] : r; }
-        else if (mode == 1) { r = 0; for (int i = 0; i < NBLK; i++) r += sh->slot[i]; }
-        else r = sh->slot[src];
-        pthread_barrier_wait(&sh->bar);
-        return (T)r;
-    }
-    template <class T> T max(T v) const { return exchange(v, 0); }
-    template <class T> T sum(T v) const { return exchange(v, 1); }
-    bool any_in_instance(bool p) const { return exchange((double)p, 0) != 0.0; }
-    bool any_in_group(bool p) const { return any_in_instance(p); }
-    template <class T> T from_block(T v, int src) const { return exchange(v, 2, src); }
-    void sync() const { if (NBLK > 1) pthread_barrier_wait(&sh->bar); }
+struct HostGroup {
+    static constexpr int L = 1;
+    int lane = 0;
+    template <class T> T max(T v) const { return v; }
+    template <class T> T sum(T v) const { return v; }
+    bool any(bool p) const { return p; }
+    bool any_warp(bool p) const { return p; }
+    void sync() const {}
 };
 
 template <class M, class T>
 struct Sim {
-    Ws<T> w; std::vector<T> buf; std::vector<int32_t> ints; int B, N;
+    Gs<T> gs; std::vector<T> buf, sm; std::vector<int32_t> ints; int B, N;
     Sim(int B_, int N_) : B(B_), N(N_) {
-        w.B = B; w.S = (size_t)((B * M::NBLK + 31) / 32) * 32;
-        const int rows = WsLayout<M>::fill(N, w.off);
-        buf.assign((size_t)rows * w.S, T(0)); w.base = buf.data();
+        constexpr int SG = M::NU + M::NX;
+        const size_t nV = (size_t)(N + 1) * SG, nPI = (size_t)N * M::NX, nL = (size_t)N * 2 * SG;
+        buf.assign((size_t)B * (2 * nV + nPI + nL + M::NX + M::NP), T(0));
+        T* p = buf.data();
+        gs.V = p; p += B * nV; gs.PI = p; p += B * nPI; gs.LAM = p; p += B * nL; gs.YREF = p; p += B * nV; gs.X0 = p; p += (size_t)B * M::NX; gs.PAR = p;
         ints.assign((size_t)4 * B, 0);
-        w.status = ints.data(); w.sqp_iter = w.status + B; w.qp_iter = w.sqp_iter + B; w.have_mult = w.qp_iter + B;
+        gs.status = ints.data(); gs.sqp_iter = gs.status + B; gs.qp_iter = gs.sqp_iter + B; gs.have_mult = gs.qp_iter + B;
+        gs.B = B; gs.N = N;
+        sm.assign(SmLayout<M>::elems(N), T(0));
+    }
+    void set(int inst, int field, int k, const double* v) {
+        const int dim = field_dim(M::NX, M::NU, M::NP, field, k, N);
+        for (int j = 0; j < dim; j++) *field_ptr(gs, M::NX, M::NU, M::NP, inst, field, k, j) = T(v[j]);
+    }
+    void get(int inst, int field, int k, double* v) {
+        const int dim = field_dim(M::NX, M::NU, M::NP, field, k, N);
+        for (int j = 0; j < dim; j++) v[j] = double(*field_ptr(gs, M::NX, M::NU, M::NP, inst, field, k, j));
     }
 };
-
-// run fn(inst, b, xchg) for every (instance, block); blocks of one instance run as concurrent host threads
-template <class M, class F>
-static void for_all(int B, F fn) {
-    constexpr int NBLK = M::NBLK;
-    for (int i = 0; i < B; i++) {
-        HostShared<NBLK> sh;
-        if (NBLK > 1) pthread_barrier_init(&sh.bar, NULL, NBLK);
-        std::vector<std::thread> th;
-        for (int b = 1; b < NBLK; b++) th.emplace_back([&, b] { HostXchg<NBLK> xc{&sh, b}; fn(i, b, xc); });
-        HostXchg<NBLK> xc{&sh, 0};
-        fn(i, 0, xc);
-        for (auto& t : th) t.join();
-        if (NBLK > 1) pthread_barrier_destroy(&sh.bar);
-    }
-}
 
 template <class M, class T>
 static int solve_batch_t(const Opts* o, int B, const double* x0, const double* yref, const double* p, double* x, double* u,
                          double* pi, int* status, int* sqp_iter, int* qp_iter) {
-    constexpr int NBLK = M::NBLK, NX = M::NX, NU = M::NU, ny = NX + NU;
+    constexpr int NX = M::NX, NU = M::NU, ny = NX + NU;
     const int N = o->N;
     Sim<M, T> sim(B, N);
-    for_all<M>(B, [&](int i, int b, HostXchg<NBLK>& xc) {
-        const size_t slot = (size_t)i * NBLK + b;
-        for (int k = 0; k <= N; k++) field_xfer<M, T, true>(sim.w, slot, b, F_X, k, N, x + ((size_t)i * (N + 1) + k) * NX);
-        for (int k = 0; k < N; k++) field_xfer<M, T, true>(sim.w, slot, b, F_U, k, N, u + ((size_t)i * N + k) * NU);
-        field_xfer<M, T, true>(sim.w, slot, b, F_LBX, 0, N, const_cast<double*>(x0) + (size_t)i * NX);
-        field_xfer<M, T, true>(sim.w, slot, b, F_P, 0, N, const_cast<double*>(p) + (size_t)i * 2);
-        yref_all_to_ws<M, T>(sim.w, slot, b, N, yref + (size_t)i * (N * ny + NX));
-        BlockSolver<M, T, HostXchg<NBLK>> bs(sim.w, *o, xc, slot, b);
-        bs.sqp_solve(true, i);
-        for (int k = 0; k <= N; k++) field_xfer<M, T, false>(sim.w, slot, b, F_X, k, N, x + ((size_t)i * (N + 1) + k) * NX);
-        for (int k = 0; k < N; k++) field_xfer<M, T, false>(sim.w, slot, b, F_U, k, N, u + ((size_t)i * N + k) * NU);
-        if (pi) for (int k = 0; k < N; k++) field_xfer<M, T, false>(sim.w, slot, b, F_PI, k, N, pi + ((size_t)i * N + k) * NX);
-    });
-    for (int i = 0; i < B; i++) { status[i] = sim.w.status[i]; sqp_iter[i] = sim.w.sqp_iter[i]; qp_iter[i] = sim.w.qp_iter[i]; }
+    HostGroup g;
+    for (int i = 0; i < B; i++) {
+        for (int k = 0; k <= N; k++) sim.set(i, F_X, k, x + ((size_t)i * (N + 1) + k) * NX);
+        for (int k = 0; k < N; k++) sim.set(i, F_U, k, u + ((size_t)i * N + k) * NU);
+        for (int k = 0; k <= N; k++) sim.set(i, F_YREF, k, yref + (size_t)i * (N * ny + NX) + (size_t)k * ny);
+        sim.set(i, F_LBX, 0, x0 + (size_t)i * NX);
+        sim.set(i, F_P, 0, p + (size_t)i * 2);
+        Solver<M, T, HostGroup> sv(sim.sm.data(), *o, g);
+        api_solve<M, T>(sv, i, sim.gs);
+        for (int k = 0; k <= N; k++) sim.get(i, F_X, k, x + ((size_t)i * (N + 1) + k) * NX);
+        for (int k = 0; k < N; k++) sim.get(i, F_U, k, u + ((size_t)i * N + k) * NU);
+        if (pi) for (int k = 0; k < N; k++) sim.get(i, F_PI, k, pi + ((size_t)i * N + k) * NX);
+        status[i] = sim.gs.status[i]; sqp_iter[i] = sim.gs.sqp_iter[i]; qp_iter[i] = sim.gs.qp_iter[i];
+    }
     return 0;
 }
 
@@ -96,10 +76,10 @@ template <class M, class T>
 static int closed_loop_t(const Opts* o, int kind, int B, int n_steps, int rows, const double* ref, int ref_shared, const double* x0,
                          const double* noise, const double* p_ctrl, const double* p_plant, double* Xsim, double* U_plant,
                          double* U_ctrl, double* a_log, double* cost, double* abs_err, int* status, int* qp_iter) {
-    constexpr int NBLK = M::NBLK;
     const int N = o->N;
     if (rows < n_steps + N) return -1;
     Sim<M, T> sim(B, N);
+    HostGroup g;
     const size_t Bp = B;
     std::vector<double> xs(4 * Bp), acc(2 * Bp), pp(2 * Bp);
     for (int i = 0; i < B; i++) {
@@ -107,21 +87,20 @@ static int closed_loop_t(const Opts* o, int kind, int B, int n_steps, int rows, 
         acc[i] = 0.0; acc[Bp + i] = p_ctrl[B + i];
         pp[i] = p_plant[i]; pp[Bp + i] = p_plant[B + i];
         cost[i] = 0; abs_err[i] = 0;
+        const double pc[2] = {p_ctrl[i], p_ctrl[B + i]};
+        sim.set(i, F_P, 0, pc);
     }
-    for_all<M>(B, [&](int i, int b, HostXchg<NBLK>& xc) {
-        const size_t slot = (size_t)i * NBLK + b;
-        double pc[2] = {p_ctrl[i], p_ctrl[B + i]};
-        field_xfer<M, T, true>(sim.w, slot, b, F_P, 0, N, pc);
-        BlockSolver<M, T, HostXchg<NBLK>> bs(sim.w, *o, xc, slot, b);
+    for (int i = 0; i < B; i++) {
+        Solver<M, T, HostGroup> sv(sim.sm.data(), *o, g);
         for (int st = 0; st < n_steps; st++) {
             LoopArgs a{};
             a.step = st; a.kind = kind; a.ref_shared = ref_shared; a.log_stride = n_steps; a.batch = B; a.Bp = Bp;
             a.ref = ref; a.noise = noise; a.Xsim = Xsim; a.U_plant = U_plant; a.U_ctrl = U_ctrl; a.a_log = a_log;
             a.status = status; a.qp_iter = qp_iter; a.xs = xs.data(); a.acc = acc.data(); a.cost = cost; a.abs_err = abs_err;
             a.p_plant = pp.data();
-            closed_loop_step<M, T>(bs, true, i, a);
+            closed_loop_step<M, T>(sv, i, sim.gs, a);
         }
-    });
+    }
     return 0;
 }
 
