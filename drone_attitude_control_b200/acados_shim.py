@@ -36,6 +36,11 @@ class BatchedAcadosOcpSolver:
             kw['horizon'] = int(N_horizon)
         kw['precision'] = _lib.FP32 if precision in ('fp32', 'float32', _lib.FP32) else _lib.FP64
         kw['rti'] = int(bool(rti))
+        if kw['precision'] == _lib.FP32:
+            # what single precision can certify: stationarity / equality / inequality residuals carry ~1e-5 of round-off,
+            # the complementarity tolerance stays at acados' 1e-6 (the multipliers of this OCP are tiny)
+            kw.setdefault('qp_tol', [1e-4, 1e-4, 1e-4, 1e-6])
+            kw.setdefault('tol', [1e-3, 1e-3, 1e-3, 1e-5])
         self.cfg = default_config(model, **kw)
         self.model = model
         self.batch = int(batch)

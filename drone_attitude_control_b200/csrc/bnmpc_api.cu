@@ -232,13 +232,9 @@ int fma_peak(double* tflops) {
     return 0;
 }
 
-// warps (= instances) per CTA: one by default (the CTA is only a packing unit; small CTAs pack shared memory best)
-int default_wpc(const Handle* h) {
-    int w = h->cfg.threads_per_block > 0 ? (h->cfg.threads_per_block + 31) / 32 : 1;
-    const size_t per = h->ops->smem_bytes(h->cfg.horizon);
-    while (w > 1 && per * w > 227 * 1024) w--;
-    return w;
-}
+// warps (= instances) per CTA: always one.  The CTA is only a packing unit (no inter-warp synchronisation), and
+// one-warp CTAs pack shared memory and registers best (the kernels are compiled with __launch_bounds__(32, 10)).
+int default_wpc(const Handle*) { return 1; }
 
 int reset_iterate(Handle* h) {
     const size_t es = h->ops->elem_size, B = h->batch;

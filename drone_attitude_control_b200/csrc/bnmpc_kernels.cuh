@@ -10,6 +10,11 @@
 
 #include "bnmpc_loop.cuh"
 
+// resident one-warp CTAs per SM the register allocator should leave room for (shared memory allows 10 force / 7 jerk)
+#ifndef BNMPC_MIN_BLOCKS
+#define BNMPC_MIN_BLOCKS 8
+#endif
+
 namespace bnmpc {
 
 // type-erased Gs<T> (identical layout for every T)
@@ -39,7 +44,7 @@ __device__ __forceinline__ T* warp_smem(int N) {
 }
 
 template <class M, class T>
-__global__ void k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o) {
+__global__ void __launch_bounds__(32, BNMPC_MIN_BLOCKS) k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o) {
     const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (inst >= gs.B) return;          // whole warp
     const WarpGroup<32> g;
@@ -48,7 +53,7 @@ __global__ void k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant_
 }
 
 template <class M, class T>
-__global__ void k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a) {
+__global__ void __launch_bounds__(32, BNMPC_MIN_BLOCKS) k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a) {
     const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (inst >= gs.B) return;          // whole warp
     const WarpGroup<32> g;
