@@ -90,19 +90,15 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': rs, 'samples': len(self.samples)}
 
 
-def make_inputs(model, B, rows, seed, device):
-    """BASELINE config 2 / SURVEY 8d inputs, generated per rank from a seed keyed by the global instance ids."""
-    import torch
+def make_inputs(lo, hi, n_steps, rows, device):
+    """BASELINE config 2 / SURVEY 8d inputs for the global instances lo..hi-1 (per-instance seeds keyed by the global id:
+    the numbers do not depend on how many ranks share the batch)."""
     from drone_attitude_control_b200.generate_trajectory import gen_circle_traj_batched
-    g = torch.Generator().manual_seed(2026 + seed)
-    u = lambda *sh: torch.rand(*sh, generator=g, dtype=torch.float64)
-    radius = 0.5 + 0.5 * u(B)
-    center = -0.15 + 0.3 * u(B, 2)
-    phase = 2 * np.pi * u(B)
-    ref = gen_circle_traj_batched(500, rows - 500, radius, center, phase, device=device)      # [rows, 8, B]
-    x0 = ref[0, :4, :].clone() + (-0.05 + 0.1 * u(4, B)).to(device)
-    noise = (0.01 * torch.randn(rows, B, generator=g, dtype=torch.float64)).to(device)
-    return ref, x0, noise
+    from drone_attitude_control_b200.sharding import instance_inputs
+    inp = instance_inputs(lo, hi, n_steps)
+    ref = gen_circle_traj_batched(500, rows - 500, inp['radius'], inp['center'], inp['phase'], device=device)      # [rows, 8, b]
+    x0 = ref[0, :4, :].clone() + inp['dx0'].to(device)
+    return ref, x0, inp['noise'].to(device)
 
 
 def run_ours(args):
@@ -122,7 +118,7 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
     N = args.horizon
     rows = max(500 + N, W + K + N + 1)
-    ref, x0, noise = make_inputs(args.model, B, rows, seed=rank, device=dev)
+    ref, x0, noise = make_inputs(rank * B, (rank + 1) * B, W + K, rows, device=dev)       # weak scaling: B instances per rank
     loop = pkg.BatchedClosedLoop(args.model, batch=B, device=local, precision=args.precision, N_horizon=N, rti=args.rti)
     loop.init(x0, ref, noise=noise, n_steps=W + K, log=True)
     stream = torch.cuda.current_stream()
@@ -325,7 +321,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--model', default='force', choices=['force', 'jerk', 'force_dense', 'jerk_dense'])
+    ap.add_argument('--model', default='force', choices=['force', 'jerk', 'force_dense'])
     ap.add_argument('--batch', type=int, default=4096, help='instances per GPU')
     ap.add_argument('--horizon', type=int, default=30)
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'])

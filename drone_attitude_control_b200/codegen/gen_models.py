@@ -96,6 +96,41 @@ def _subs_arrays(exprs, xs, us, ps, xmap=None, umap=None):
     return [sp.sympify(e).subs(d) for e in exprs]
 
 
+_ERK_TABLEAUS = {
+    1: ([[0]], [1]),
+    2: ([[0, 0], [sp.Rational(1, 2), 0]], [0, 1]),
+    3: ([[0, 0, 0], [sp.Rational(1, 2), 0, 0], [-1, 2, 0]], [sp.Rational(1, 6), sp.Rational(2, 3), sp.Rational(1, 6)]),
+    4: ([[0, 0, 0, 0], [sp.Rational(1, 2), 0, 0, 0], [0, sp.Rational(1, 2), 0, 0], [0, 0, 1, 0]],
+        [sp.Rational(1, 6), sp.Rational(1, 3), sp.Rational(1, 3), sp.Rational(1, 6)]),
+}
+
+
+def _sens_structure(xs, us, f, comps):
+    """Structural zeros / ones of the discrete-time sensitivities A = d x+/d x, B = d x+/d u of one explicit RK step,
+    valid for every stage count 1..4, every step size and every block (the intersection is emitted, so the flags do not
+    depend on run-time options).  Only used for constant-Jacobian models."""
+    h = sp.Symbol('h', positive=True)
+    nxb, nub = len(comps[0][0]), len(comps[0][1])
+    a_zero = [[True] * nxb for _ in range(nxb)]; a_one = [[True] * nxb for _ in range(nxb)]
+    b_zero = [[True] * nub for _ in range(nxb)]
+    for cx, cu in comps:
+        xb = [xs[i] for i in cx]; ub = [us[i] for i in cu]; fb = [f[i] for i in cx]
+        for ns, (At, bt) in _ERK_TABLEAUS.items():
+            K = []
+            for i in range(ns):
+                xi = [xb[r] + h * sum(At[i][j] * K[j][r] for j in range(i)) for r in range(nxb)]
+                K.append([sp.expand(e.subs(dict(zip(xb, xi)), simultaneous=True)) for e in fb])
+            xn = [sp.expand(xb[r] + h * sum(bt[i] * K[i][r] for i in range(ns))) for r in range(nxb)]
+            A = sp.Matrix(xn).jacobian(sp.Matrix(xb)); B = sp.Matrix(xn).jacobian(sp.Matrix(ub))
+            for r in range(nxb):
+                for c in range(nxb):
+                    e = sp.simplify(A[r, c])
+                    a_zero[r][c] &= (e == 0); a_one[r][c] &= (e == 1)
+                for c in range(nub):
+                    b_zero[r][c] &= (sp.simplify(B[r, c]) == 0)
+    return a_zero, a_one, b_zero
+
+
 def gen_model(name, xs, us, ps, f, force_single_block=False):
     nx, nu, npar = len(xs), len(us), len(ps)
     f = [sp.sympify(e) for e in f]
@@ -116,6 +151,19 @@ def gen_model(name, xs, us, ps, f, force_single_block=False):
     L.append('    static constexpr int NBLK = %d, NXB = %d, NUB = %d;' % (nblk, nxb, nub))
     L.append('    static constexpr bool JAC_CONST = %s;' % ('true' if jac_const else 'false'))
     L.append('    static constexpr const char* name() { return "%s"; }' % name)
+    if jac_const:
+        a_zero, a_one, b_zero = _sens_structure(xs, us, f, comps)
+    else:
+        a_zero = [[False] * nxb for _ in range(nxb)]; a_one = [[False] * nxb for _ in range(nxb)]
+        b_zero = [[False] * max(nub, 1) for _ in range(nxb)]
+    L.append('    // structure of the discrete-time sensitivities A (NXB x NXB), B (NXB x NUB) of one ERK step, found symbolically:')
+    L.append('    // entries that are identically 0 / 1 for every stage count, step size and block (all false if not constant)')
+    for nm, tab, nc in (('a_zero', a_zero, nxb), ('a_one', a_one, nxb), ('b_zero', b_zero, max(nub, 1))):
+        rows = ', '.join('{' + ', '.join('true' if v else 'false' for v in row) + '}' for row in tab)
+        L.append('    __host__ __device__ static constexpr bool %s(int r, int c) {' % nm)
+        L.append('        constexpr bool tab[%d][%d] = {%s};' % (nxb, nc, rows))
+        L.append('        return tab[r][c];')
+        L.append('    }')
     for nm, idx in (('xg', 0), ('ug', 1)):
         n_loc = nxb if idx == 0 else nub
         rows = ', '.join('{' + ', '.join(str(i) for i in c[idx]) + '}' for c in comps)

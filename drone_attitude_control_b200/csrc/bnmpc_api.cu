@@ -1,6 +1,7 @@
 // bnmpc_api.cu - the C-ABI of include/bnmpc.h: handle, workspace, staging, kernel launches.  No solver arithmetic here.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -27,7 +28,8 @@ struct Handle {
     bnmpc_config cfg;
     Opts opts;
     const ModelOps* ops;
-    int batch, device, wpc;        // wpc: warps (= instances) per CTA
+    int batch, device, ctas;       // ctas: persistent CTAs per launch
+    int *queue, qi;                // work-queue counters (one per launch, recycled), next counter to use
     cudaStream_t stream;
     bool own_stream;
     GsAny gs;                      // persistent per-instance state in HBM
@@ -47,7 +49,6 @@ const ModelOps* pick_ops(int model, int precision) {
     case BNMPC_MODEL_FORCE: return ops_force(precision);
     case BNMPC_MODEL_JERK: return ops_jerk(precision);
     case BNMPC_MODEL_FORCE_DENSE: return ops_force_dense(precision);
-    case BNMPC_MODEL_JERK_DENSE: return ops_jerk_dense(precision);
     }
     return nullptr;
 }
@@ -232,9 +233,17 @@ int fma_peak(double* tflops) {
     return 0;
 }
 
-// warps (= instances) per CTA: always one.  The CTA is only a packing unit (no inter-warp synchronisation), and
-// one-warp CTAs pack shared memory and registers best (the kernels are compiled with __launch_bounds__(32, 10)).
-int default_wpc(const Handle*) { return 1; }
+constexpr int QUEUE_LEN = 1024;
+
+// counter of the work queue for the next launch; the ring is re-zeroed (stream-ordered) when it wraps
+int next_queue(Handle* h, int** q) {
+    if (h->qi == QUEUE_LEN) {
+        CK(cudaMemsetAsync(h->queue, 0, sizeof(int) * QUEUE_LEN, h->stream));
+        h->qi = 0;
+    }
+    *q = h->queue + h->qi++;
+    return 0;
+}
 
 int reset_iterate(Handle* h) {
     const size_t es = h->ops->elem_size, B = h->batch;
@@ -254,9 +263,9 @@ const char* bnmpc_last_error(void) { return g_err.c_str(); }
 
 int bnmpc_config_default(int model, bnmpc_config* c) {
     if (!c) return fail(BNMPC_E_ARG, "cfg is NULL");
-    if (model < 0 || model > BNMPC_MODEL_JERK_DENSE) return fail(BNMPC_E_ARG, "unknown model");
+    if (model < 0 || model > BNMPC_MODEL_FORCE_DENSE) return fail(BNMPC_E_ARG, "unknown model");
     memset(c, 0, sizeof(*c));
-    const bool jerk = (model == BNMPC_MODEL_JERK || model == BNMPC_MODEL_JERK_DENSE);
+    const bool jerk = (model == BNMPC_MODEL_JERK);
     // reference src/params.py:37-61,113-122
     const double MASS = 0.03277, G = 9.81, GR = G * MASS;
     c->model = model; c->horizon = 30; c->precision = BNMPC_FP64; c->sqp_max_iter = 100; c->qp_max_iter = 50; c->rti = 0;
@@ -305,7 +314,10 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete h; return fail(BNMPC_E_CUDA, cudaGetErrorString(e)); }
     h->own_stream = true;
-    if (ops->smem_bytes(cfg->horizon) > 227 * 1024) { delete h; return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of one instance exceeds 227 KB of shared memory"); }
+    if (ops->smem_bytes(cfg->horizon) * BNMPC_WARPS_PER_CTA > 226 * 1024 || ops->tmem_cols(cfg->horizon) == 0) {
+        delete h;
+        return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of a CTA exceeds 227 KB of shared memory or 512 tensor-memory columns");
+    }
     const size_t SGd = ops->nu + ops->nx, Nn = cfg->horizon, es = ops->elem_size;
     h->nV = (Nn + 1) * SGd; h->nPI = Nn * ops->nx; h->nLAM = Nn * 2 * SGd;
     const size_t per = 2 * h->nV + h->nPI + h->nLAM + ops->nx + ops->np;
@@ -313,6 +325,7 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     h->Bp = ((size_t)batch + 31) / 32 * 32;
     bool ok = cudaMalloc(&h->gs_base, h->gs_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&h->ints, sizeof(int32_t) * 4 * batch) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->queue, sizeof(int) * QUEUE_LEN) == cudaSuccess;
     ok = ok && cudaMalloc(&h->xs, sizeof(double) * 11 * h->Bp) == cudaSuccess;
     if (!ok) {
         const std::string msg = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -327,7 +340,21 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     }
     h->gs.status = h->ints; h->gs.sqp_iter = h->ints + batch; h->gs.qp_iter = h->ints + 2 * batch; h->gs.have_mult = h->ints + 3 * batch;
     h->gs.B = batch; h->gs.N = cfg->horizon;
-    h->wpc = default_wpc(h);
+    {
+        int per_sm = 0;
+        cudaDeviceProp pr;
+        CK(cudaGetDeviceProperties(&pr, device));
+        CK(ops->max_ctas_per_sm(cfg->horizon, &per_sm));
+        if (per_sm < 1) { bnmpc_destroy(h); return fail(BNMPC_E_UNSUPPORTED, "kernel does not fit on an SM for this horizon"); }
+        if (const char* e = getenv("BNMPC_CTAS_PER_SM")) {      // tuning knob: fewer resident CTAs per SM than would fit
+            const int v = atoi(e);
+            if (v >= 1 && v < per_sm) per_sm = v;
+        }
+        const int want = (batch + BNMPC_WARPS_PER_CTA - 1) / BNMPC_WARPS_PER_CTA;
+        h->ctas = want < per_sm * pr.multiProcessorCount ? want : per_sm * pr.multiProcessorCount;
+    }
+    CK(cudaMemsetAsync(h->queue, 0, sizeof(int) * QUEUE_LEN, h->stream));
+    h->qi = 0;
     CK(cudaMemsetAsync(h->gs_base, 0, h->gs_bytes, h->stream));
     CK(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * batch, h->stream));
     CK(cudaMemsetAsync(h->xs, 0, sizeof(double) * 11 * h->Bp, h->stream));
@@ -348,6 +375,7 @@ int bnmpc_destroy(void* handle) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->gs_base) cudaFree(h->gs_base);
     if (h->ints) cudaFree(h->ints);
+    if (h->queue) cudaFree(h->queue);
     if (h->xs) cudaFree(h->xs);
     for (int i = 0; i < 4; i++) if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -442,7 +470,9 @@ int bnmpc_solve(void* handle) {
     Handle* h = (Handle*)handle;
     if (!h) return fail(BNMPC_E_ARG, "NULL handle");
     if (use_device(h)) return BNMPC_E_CUDA;
-    CK(h->ops->solve(h->gs, h->opts, h->wpc, h->stream)); h->launches++;
+    int* q;
+    if (int rc = next_queue(h, &q)) return rc;
+    CK(h->ops->solve(h->gs, h->opts, h->ctas, q, h->stream)); h->launches++;
     return 0;
 }
 
@@ -521,7 +551,9 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     la.xs = h->xs; la.acc = h->acc; la.cost = h->cost; la.abs_err = h->abs_err; la.p_plant = h->p_plant;
     for (int s = 0; s < a->n_steps; s++) {
         la.step = a->first_step + s;
-        CK(h->ops->loop_step(h->gs, h->opts, la, h->wpc, h->stream)); h->launches++;
+        int* q;
+        if (int rc = next_queue(h, &q)) return rc;
+        CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, q, h->stream)); h->launches++;
     }
     return 0;
 }

@@ -2,18 +2,28 @@
 // Each model_*.cu instantiates BNMPC_DEFINE_MODEL_OPS for one generated model (both precisions); bnmpc_api.cu only
 // sees the ModelOps table, so the heavy templates compile in parallel translation units.
 //
-// Launch shape: one warp per OCP instance, `wpc` warps per CTA, each warp with its own slice of dynamic shared memory
-// (SmLayout<M>::elems(N) elements).  There is no inter-warp synchronisation; the CTA is only a packing unit.
+// Launch shape: PERSISTENT CTAs of 4 warps; every warp pulls OCP instances from an atomic work queue and solves them
+// one at a time (instance solve lengths differ by 4x, so the queue balances itself).  Warps of a CTA never synchronise
+// during the solves; the CTA exists because of tensor memory:
+//
+//   * shared memory holds the part of an instance's working set that the Riccati sweeps and neighbouring stages touch
+//     (SmLayout<M,false>: 27 doubles per (stage, block) item for the force model, 13.4 KB per instance);
+//   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t: 15 doubles per item).  A warp
+//     owns the 32 TMEM lanes of its quarter; lane l keeps the records of its items in consecutive columns and moves a
+//     whole record with one tcgen05.ld / tcgen05.st (.32x32b.x32).  TMEM is used purely as a software-managed,
+//     lane-private scratchpad - no tcgen05.mma is involved: these are 3x3 / 4x4 FP64 problems.
+//
+// This doubles the instances in flight per SM (16 instead of 8-10), which is what bounds this latency-bound solver.
 #pragma once
 #include <cuda_runtime.h>
 #include <string.h>
 
 #include "bnmpc_loop.cuh"
 
-// resident one-warp CTAs per SM the register allocator should leave room for (shared memory allows 10 force / 7 jerk)
-#ifndef BNMPC_MIN_BLOCKS
-#define BNMPC_MIN_BLOCKS 8
+#ifndef BNMPC_CTAS_PER_SM
+#define BNMPC_CTAS_PER_SM 4
 #endif
+#define BNMPC_WARPS_PER_CTA 4
 
 namespace bnmpc {
 
@@ -31,66 +41,202 @@ template <class T> inline Gs<T> gs_cast(const GsAny& a) {
 struct ModelOps {
     const char* name;
     int nx, nu, np, nblk, nxb, nub, kind, jac_const, elem_size, sm_rows;
-    size_t (*smem_bytes)(int N);                                    // dynamic shared memory of one instance
-    cudaError_t (*solve)(const GsAny&, const Opts&, int wpc, cudaStream_t);
-    cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int wpc, cudaStream_t);
+    size_t (*smem_bytes)(int N);                                    // dynamic shared memory of one instance (one warp)
+    int (*tmem_cols)(int N);                                        // tensor-memory columns one CTA allocates (0 = too many)
+    cudaError_t (*solve)(const GsAny&, const Opts&, int ctas, int* queue, cudaStream_t);
+    cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int* queue, cudaStream_t);
+    cudaError_t (*max_ctas_per_sm)(int N, int* out);
 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tensor memory as lane-private storage
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* w) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]),
+          "=r"(w[8]), "=r"(w[9]), "=r"(w[10]), "=r"(w[11]), "=r"(w[12]), "=r"(w[13]), "=r"(w[14]), "=r"(w[15]),
+          "=r"(w[16]), "=r"(w[17]), "=r"(w[18]), "=r"(w[19]), "=r"(w[20]), "=r"(w[21]), "=r"(w[22]), "=r"(w[23]),
+          "=r"(w[24]), "=r"(w[25]), "=r"(w[26]), "=r"(w[27]), "=r"(w[28]), "=r"(w[29]), "=r"(w[30]), "=r"(w[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* w) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+        :: "r"(taddr),
+           "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]),
+           "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15]),
+           "r"(w[16]), "r"(w[17]), "r"(w[18]), "r"(w[19]), "r"(w[20]), "r"(w[21]), "r"(w[22]), "r"(w[23]),
+           "r"(w[24]), "r"(w[25]), "r"(w[26]), "r"(w[27]), "r"(w[28]), "r"(w[29]), "r"(w[30]), "r"(w[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
+__device__ __forceinline__ double words_to(uint32_t lo, uint32_t hi, double) { return __hiloint2double((int)hi, (int)lo); }
+__device__ __forceinline__ float words_to(uint32_t lo, uint32_t, float) { return __uint_as_float(lo); }
+
+template <class M, class T>
+struct TmemPriv {
+    static constexpr bool IN_SMEM = false;
+    static constexpr int s = M::NXB + M::NUB;
+    static constexpr int WPE = (int)sizeof(T) / 4;                 // 32-bit words per element
+    static constexpr int NE = 5 * s;                               // elements of a record: q, lam, t
+    static constexpr int CH = (NE * WPE + 31) / 32;                // .x32 chunks per record
+    static constexpr int CPR = CH * 32;                            // columns per round of items
+    uint32_t base;                                                 // lane quarter of this warp | first column
+
+    static __host__ __device__ int cols_needed(int N) {            // power of two >= 32, 0 if it does not fit
+        const int rounds = ((N + 1) * M::NBLK + 31) / 32;
+        const int need = rounds * CPR;
+        int c = 32;
+        while (c < need) c <<= 1;
+        return c <= 512 ? c : 0;
+    }
+    __device__ __forceinline__ void load(T*, int rd, int, bool, PrivRec<T, s>& r) const {
+        __syncwarp();                                              // tcgen05.ld/st are warp-collective (.aligned)
+        uint32_t w[CH * 32];
+#pragma unroll
+        for (int c = 0; c < CH; c++) tmem_ld32(base + rd * CPR + c * 32, w + c * 32);
+        tmem_wait_ld();
+        T e[NE];
+#pragma unroll
+        for (int i = 0; i < NE; i++) e[i] = words_to(w[i * WPE], w[i * WPE + WPE - 1], T());
+#pragma unroll
+        for (int v = 0; v < s; v++) r.q[v] = e[v];
+#pragma unroll
+        for (int v = 0; v < 2 * s; v++) { r.lam[v] = e[s + v]; r.tt[v] = e[3 * s + v]; }
+    }
+    __device__ __forceinline__ void store(T*, int rd, int, bool, const PrivRec<T, s>& r) const {
+        T e[NE];
+#pragma unroll
+        for (int v = 0; v < s; v++) e[v] = r.q[v];
+#pragma unroll
+        for (int v = 0; v < 2 * s; v++) { e[s + v] = r.lam[v]; e[3 * s + v] = r.tt[v]; }
+        uint32_t w[CH * 32];
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < CH * 32; i++) w[i] = 0u;
+#pragma unroll
+        for (int i = 0; i < NE; i++) {
+            if constexpr (WPE == 2) { w[2 * i] = (uint32_t)__double2loint((double)e[i]); w[2 * i + 1] = (uint32_t)__double2hiint((double)e[i]); }
+            else w[i] = __float_as_uint((float)e[i]);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) tmem_st32(base + rd * CPR + c * 32, w + c * 32);
+        tmem_wait_st();
+    }
+};
+
+// per-CTA tensor memory allocation (warp 0 allocates and frees; the address travels through shared memory)
+__device__ __forceinline__ uint32_t tmem_alloc_cta(uint32_t cols) {
+    __shared__ uint32_t tmem_base_s;
+    if ((threadIdx.x >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n"
+                     :: "r"((uint32_t)__cvta_generic_to_shared(&tmem_base_s)), "r"(cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    return tmem_base_s;
+}
+__device__ __forceinline__ void tmem_free_cta(uint32_t base, uint32_t cols) {
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" :: "r"(base), "r"(cols) : "memory");
+}
 
 template <class M, class T>
 __device__ __forceinline__ T* warp_smem(int N) {
     extern __shared__ double4 smem_raw[];
-    const size_t per = (SmLayout<M>::elems(N) * sizeof(T) + 15) / 16 * 16;
+    const size_t per = (SmLayout<M, false>::elems(N) * sizeof(T) + 15) / 16 * 16;
     return reinterpret_cast<T*>(reinterpret_cast<char*>(smem_raw) + per * (threadIdx.x >> 5));
 }
 
-template <class M, class T>
-__global__ void __launch_bounds__(32, BNMPC_MIN_BLOCKS) k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o) {
-    const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (inst >= gs.B) return;          // whole warp
-    const WarpGroup<32> g;
-    Solver<M, T, WarpGroup<32>> sv(warp_smem<M, T>(o.N), o, g);
-    api_solve<M, T>(sv, inst, gs);
+// next instance of the work queue (one atomic per warp)
+__device__ __forceinline__ int next_instance(int* queue) {
+    int i = 0;
+    if ((threadIdx.x & 31) == 0) i = atomicAdd(queue, 1);
+    return __shfl_sync(0xffffffffu, i, 0);
 }
 
 template <class M, class T>
-__global__ void __launch_bounds__(32, BNMPC_MIN_BLOCKS) k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a) {
-    const int inst = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (inst >= gs.B) return;          // whole warp
+__global__ void __launch_bounds__(32 * BNMPC_WARPS_PER_CTA, BNMPC_CTAS_PER_SM)
+k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, int* queue, int tmem_cols) {
+    const uint32_t tbase = tmem_alloc_cta(tmem_cols);
     const WarpGroup<32> g;
-    Solver<M, T, WarpGroup<32>> sv(warp_smem<M, T>(o.N), o, g);
-    closed_loop_step<M, T>(sv, inst, gs, a);
+    const TmemPriv<M, T> ps{tbase + (((threadIdx.x >> 5) * 32u) << 16)};
+    Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(warp_smem<M, T>(o.N), o, g, ps);
+    for (int inst = next_instance(queue); inst < gs.B; inst = next_instance(queue)) api_solve<M, T>(sv, inst, gs);
+    tmem_free_cta(tbase, tmem_cols);
+}
+
+template <class M, class T>
+__global__ void __launch_bounds__(32 * BNMPC_WARPS_PER_CTA, BNMPC_CTAS_PER_SM)
+k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a, int* queue, int tmem_cols) {
+    const uint32_t tbase = tmem_alloc_cta(tmem_cols);
+    const WarpGroup<32> g;
+    const TmemPriv<M, T> ps{tbase + (((threadIdx.x >> 5) * 32u) << 16)};
+    Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(warp_smem<M, T>(o.N), o, g, ps);
+    for (int inst = next_instance(queue); inst < gs.B; inst = next_instance(queue)) closed_loop_step<M, T>(sv, inst, gs, a);
+    tmem_free_cta(tbase, tmem_cols);
 }
 
 template <class M, class T>
 struct OpsImpl {
-    static size_t smem_bytes(int N) { return (SmLayout<M>::elems(N) * sizeof(T) + 15) / 16 * 16; }
+    static size_t smem_bytes(int N) { return (SmLayout<M, false>::elems(N) * sizeof(T) + 15) / 16 * 16; }
+    static int tmem_cols(int N) { return TmemPriv<M, T>::cols_needed(N); }
+    // dynamic shared memory is opted in once per kernel up to the device limit (handles with different horizons share
+    // the kernel, so the attribute must not follow the last handle created)
     template <class K>
-    static cudaError_t prep(K kern, size_t bytes) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    static cudaError_t prep(K kern, size_t) {
+        int dev = 0, optin = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);   // minus the static part
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    static cudaError_t solve(const GsAny& a, const Opts& o, int wpc, cudaStream_t st) {
-        const size_t bytes = smem_bytes(o.N) * wpc;
-        cudaError_t e = prep(k_solve<M, T>, bytes);
+    static cudaError_t max_ctas_per_sm(int N, int* out) {
+        const size_t bytes = smem_bytes(N) * BNMPC_WARPS_PER_CTA;
+        cudaError_t e = prep(k_loop_step<M, T>, bytes);
         if (e != cudaSuccess) return e;
-        k_solve<M, T><<<(a.B + wpc - 1) / wpc, 32 * wpc, bytes, st>>>(gs_cast<T>(a), o);
+        e = prep(k_solve<M, T>, bytes);
+        if (e != cudaSuccess) return e;
+        // resident CTAs per SM: registers (the launch bound), shared memory (228 KB per SM, 1 KB reserved per CTA) and
+        // tensor memory (512 columns per SM; every resident CTA must get its columns or tcgen05.alloc would block)
+        int dev = 0, smem_sm = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        if (e != cudaSuccess) return e;
+        int r = BNMPC_CTAS_PER_SM;
+        const int by_smem = (int)((size_t)smem_sm / (bytes + 1024));
+        if (by_smem < r) r = by_smem;
+        const int cols = tmem_cols(N);
+        if (cols > 0 && 512 / cols < r) r = 512 / cols;
+        *out = r;
+        return cudaSuccess;
+    }
+    static cudaError_t solve(const GsAny& a, const Opts& o, int ctas, int* queue, cudaStream_t st) {
+        k_solve<M, T><<<ctas, 32 * BNMPC_WARPS_PER_CTA, smem_bytes(o.N) * BNMPC_WARPS_PER_CTA, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N));
         return cudaGetLastError();
     }
-    static cudaError_t loop_step(const GsAny& a, const Opts& o, const LoopArgs& la, int wpc, cudaStream_t st) {
-        const size_t bytes = smem_bytes(o.N) * wpc;
-        static size_t prepared = 0;
-        if (prepared != bytes) {
-            cudaError_t e = prep(k_loop_step<M, T>, bytes);
-            if (e != cudaSuccess) return e;
-            prepared = bytes;
-        }
-        k_loop_step<M, T><<<(a.B + wpc - 1) / wpc, 32 * wpc, bytes, st>>>(gs_cast<T>(a), o, la);
+    static cudaError_t loop_step(const GsAny& a, const Opts& o, const LoopArgs& la, int ctas, int* queue, cudaStream_t st) {
+        k_loop_step<M, T><<<ctas, 32 * BNMPC_WARPS_PER_CTA, smem_bytes(o.N) * BNMPC_WARPS_PER_CTA, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N));
         return cudaGetLastError();
     }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        SmLayout<M>::ROWS, &smem_bytes, &solve, &loop_step};
+                        SmLayout<M, false>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &max_ctas_per_sm};
     }
 };
 
@@ -106,6 +252,5 @@ struct OpsImpl {
 const ModelOps* ops_force(int precision);
 const ModelOps* ops_jerk(int precision);
 const ModelOps* ops_force_dense(int precision);
-const ModelOps* ops_jerk_dense(int precision);
 
 }  // namespace bnmpc

@@ -69,9 +69,9 @@ struct LoopArgs {
 };
 
 // one instance, one control step, executed by the lanes of the solver's group
-template <class M, class T, class G>
-BN_HD void closed_loop_step(Solver<M, T, G>& sv, int inst, const Gs<T>& gs, const LoopArgs& a) {
-    using SL = SmLayout<M>;
+template <class M, class T, class G, class PS>
+BN_HD void closed_loop_step(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs, const LoopArgs& a) {
+    using SL = typename Solver<M, T, G, PS>::SL;
     constexpr int n = M::NXB, m = M::NUB, NX = M::NX, NU = M::NU, NBLK = M::NBLK, NP = M::NP;
     const size_t Bp = a.Bp, Bt = (size_t)a.batch;
     YrefSrc ys;
@@ -142,8 +142,8 @@ BN_HD void closed_loop_step(Solver<M, T, G>& sv, int inst, const Gs<T>& gs, cons
 }
 
 // one instance, one ocp_solver.solve() with the x0 / yref / p stored through the API
-template <class M, class T, class G>
-BN_HD void api_solve(Solver<M, T, G>& sv, int inst, const Gs<T>& gs) {
+template <class M, class T, class G, class PS>
+BN_HD void api_solve(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     YrefSrc ys;
     ys.ref = nullptr; ys.ref_stride = 0; ys.ref_off = 0; ys.row0 = 0;

@@ -28,12 +28,11 @@ extern "C" {
 
 #define BNMPC_VERSION 100
 
-/* models (reference src/force_model/dynamics.py:12-47, src/jerk_model/dynamics.py:12-52).  The *_DENSE variants
- * solve the same OCP without exploiting the x/z block structure (generic coupled path; cross-check). */
+/* models (reference src/force_model/dynamics.py:12-47, src/jerk_model/dynamics.py:12-52).  FORCE_DENSE solves the
+ * force-model OCP without exploiting the x/z block structure (the generic coupled path; in-product cross-check). */
 #define BNMPC_MODEL_FORCE 0
 #define BNMPC_MODEL_JERK 1
 #define BNMPC_MODEL_FORCE_DENSE 2
-#define BNMPC_MODEL_JERK_DENSE 3
 
 #define BNMPC_FP64 0
 #define BNMPC_FP32 1

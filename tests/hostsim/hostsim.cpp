@@ -21,7 +21,7 @@ struct HostGroup {
     template <class T> T max(T v) const { return v; }
     template <class T> T sum(T v) const { return v; }
     bool any(bool p) const { return p; }
-    bool any_warp(bool p) const { return p; }
+    bool all(bool p) const { return p; }
     void sync() const {}
 };
 
@@ -37,7 +37,7 @@ struct Sim {
         ints.assign((size_t)4 * B, 0);
         gs.status = ints.data(); gs.sqp_iter = gs.status + B; gs.qp_iter = gs.sqp_iter + B; gs.have_mult = gs.qp_iter + B;
         gs.B = B; gs.N = N;
-        sm.assign(SmLayout<M>::elems(N), T(0));
+        sm.assign(SmLayout<M, true>::elems(N), T(0));
     }
     void set(int inst, int field, int k, const double* v) {
         const int dim = field_dim(M::NX, M::NU, M::NP, field, k, N);
@@ -62,7 +62,8 @@ static int solve_batch_t(const Opts* o, int B, const double* x0, const double* y
         for (int k = 0; k <= N; k++) sim.set(i, F_YREF, k, yref + (size_t)i * (N * ny + NX) + (size_t)k * ny);
         sim.set(i, F_LBX, 0, x0 + (size_t)i * NX);
         sim.set(i, F_P, 0, p + (size_t)i * 2);
-        Solver<M, T, HostGroup> sv(sim.sm.data(), *o, g);
+        const SmemPriv<M, T> ps;
+        Solver<M, T, HostGroup, SmemPriv<M, T>> sv(sim.sm.data(), *o, g, ps);
         api_solve<M, T>(sv, i, sim.gs);
         for (int k = 0; k <= N; k++) sim.get(i, F_X, k, x + ((size_t)i * (N + 1) + k) * NX);
         for (int k = 0; k < N; k++) sim.get(i, F_U, k, u + ((size_t)i * N + k) * NU);
@@ -91,7 +92,8 @@ static int closed_loop_t(const Opts* o, int kind, int B, int n_steps, int rows, 
         sim.set(i, F_P, 0, pc);
     }
     for (int i = 0; i < B; i++) {
-        Solver<M, T, HostGroup> sv(sim.sm.data(), *o, g);
+        const SmemPriv<M, T> ps;
+        Solver<M, T, HostGroup, SmemPriv<M, T>> sv(sim.sm.data(), *o, g, ps);
         for (int st = 0; st < n_steps; st++) {
             LoopArgs a{};
             a.step = st; a.kind = kind; a.ref_shared = ref_shared; a.log_stride = n_steps; a.batch = B; a.Bp = Bp;

@@ -17,7 +17,7 @@ from oracle import nmpc_oracle as o
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 X0_MAIN = np.array([1.0, 0.0, 0.0, 0.62])         # reference src/main.py:45
-MODEL_ID = {'force': 0, 'jerk': 1, 'force_dense': 0, 'jerk_dense': 1}
+MODEL_ID = {'force': 0, 'jerk': 1, 'force_dense': 0}
 
 
 def _gold_err(series, g, name):
@@ -35,7 +35,7 @@ def _run_loop(model, refs, x0, noise, pc, pp, S, **kw):
     return r, loop
 
 
-@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense', 'jerk_dense'])
+@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense'])
 def test_single_solves_match_oracle(model):
     B = 96
     om = MODEL_ID[model]
@@ -61,7 +61,7 @@ def test_single_solves_match_oracle(model):
     assert rel.max() < 1e-6                                        # the north-star's bound, with a wide margin
 
 
-@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense', 'jerk_dense'])
+@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense'])
 def test_closed_loop_matches_oracle(model):
     B, S = 48, 40
     om = MODEL_ID[model]
