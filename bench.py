@@ -119,8 +119,9 @@ def run_ours(args):
     N = args.horizon
     rows = max(500 + N, W + K + N + 1)
     ref, x0, noise = make_inputs(rank * B, (rank + 1) * B, W + K, rows, device=dev)       # weak scaling: B instances per rank
+    ref_im = ref.permute(2, 0, 1).contiguous()                                             # [B, rows, 8] instance-major
     loop = pkg.BatchedClosedLoop(args.model, batch=B, device=local, precision=args.precision, N_horizon=N, rti=args.rti)
-    loop.init(x0, ref, noise=noise, n_steps=W + K, log=True)
+    loop.init(x0, ref_im, noise=noise, n_steps=W + K, log=True)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
 
@@ -167,7 +168,7 @@ def run_ours(args):
                                        numpy_io=False)
         ny, nx, nu = s.ny, s.nx, s.nu
         Ke = min(K, args.e2e_steps)
-        ref_h = ref.permute(2, 0, 1).contiguous().cpu()           # [B, rows, 8]
+        ref_h = ref_im.cpu()                                      # [B, rows, 8]
         ycols = list(range(nx)) + [nx + j for j in range(nu)] if nx == 6 else [0, 1, 2, 3, 4, 5]
         yh = [torch.cat([ref_h[:, i:i + N, ycols].reshape(B, N * ny), ref_h[:, i + N, :nx]], 1).contiguous().pin_memory()
               for i in range(W + Ke)]
@@ -220,9 +221,10 @@ def run_ours(args):
     ach_tf = fl / (ms_launch * 1e-3) * 1e-12
     ach_gbs = by / (ms_launch * 1e-3) * 1e-9
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(f'{args.model}_{args.precision}_B{B}')
+    traffic, ncu_view = None, None
+    try:       # dram bytes per launch and pipe utilisation of the dominant kernel from the committed ncu capture of this config
+        ncu_view = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(f'{args.model}_{args.precision}_B{B}')
+        traffic = ncu_view.get('traffic_bytes') if ncu_view else None
     except Exception:
         pass
     line = {
@@ -244,7 +246,7 @@ def run_ours(args):
         'roofline': {'bound': 'fp64' if args.precision == 'fp64' else 'fp32', 'achieved': ach_tf, 'peak': tf.value, 'unit': 'TFLOP/s',
                      'frac': ach_tf / tf.value if tf.value else None, 'traffic': traffic,
                      'peak_source': 'measured live: bnmpc_measure_fma_peak (MEASURED_PEAKS.json has no vector-pipe figure)',
-                     'kernel': 'k_loop_step', 'flops_per_launch': fl, 'ms_per_launch': ms_launch,
+                     'kernel': 'k_loop_step', 'flops_per_launch': fl, 'ms_per_launch': ms_launch, 'ncu': ncu_view,
                      'hbm': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
                              'bytes_per_launch': by,
                              'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650'}},
@@ -293,7 +295,7 @@ def run_reference(args):
     model = co.MODEL_JERK if args.model.startswith('jerk') else co.MODEL_FORCE
     cores = co.lib().orc_num_cores()
     K, W = args.steps, args.warmup
-    Bs = args.cpu_instances
+    Bs = min(args.cpu_instances, args.batch)
     refs, x0, noise, pp = cpu_inputs(args, Bs, W + K)
     opts = co.default_opts(model, N=args.horizon, rti=args.rti)
     # warm-up steps, then K timed steps continuing the same closed loop (the oracle API runs whole loops: time the
@@ -330,8 +332,8 @@ def main():
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=50)
-    ap.add_argument('--cpu-instances', type=int, default=1024)
-    ap.add_argument('--cpu-steps', type=int, default=50)
+    ap.add_argument('--cpu-instances', type=int, default=4096)
+    ap.add_argument('--cpu-steps', type=int, default=300, help='closed-loop steps of the cpu_baseline sample (~10 s on 16 cores)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

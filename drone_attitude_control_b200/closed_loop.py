@@ -35,17 +35,22 @@ class BatchedClosedLoop:
         return t
 
     def init(self, x0, ref, noise=None, p_ctrl=None, p_plant=None, n_steps=None, log=True):
-        """x0 [4, B]; ref [rows, 8] (shared) or [rows, 8, B]; noise [n_steps, B] or None; p_ctrl / p_plant [2, B] or None
-        (nominal mass 0.03277, g 9.81).  All batch-minor, float64."""
+        """x0 [4, B]; ref [rows, 8] (one table shared by all drones), [rows, 8, B] (batch-minor) or [B, rows, 8]
+        (instance-major, preferred: a warp reads its window contiguously); noise [n_steps, B] or None; p_ctrl / p_plant
+        [2, B] or None (nominal mass 0.03277, g 9.81).  float64."""
         B = self.batch
         self.x0 = self._dev(x0, (4, B))
         self.ref = self._dev(ref)
         if self.ref.dim() == 2:
             assert self.ref.shape[1] == 8
+            self.ref_layout, self.ref_rows = 1, int(self.ref.shape[0])
+        elif tuple(self.ref.shape[1:]) == (8, B):
+            self.ref_layout, self.ref_rows = 0, int(self.ref.shape[0])
         else:
-            assert tuple(self.ref.shape[1:]) == (8, B)
-        self.n_steps = int(n_steps if n_steps is not None else self.ref.shape[0] - self.N)
-        assert self.ref.shape[0] >= self.n_steps + self.N
+            assert self.ref.shape[0] == B and self.ref.shape[2] == 8, tuple(self.ref.shape)
+            self.ref_layout, self.ref_rows = 2, int(self.ref.shape[1])
+        self.n_steps = int(n_steps if n_steps is not None else self.ref_rows - self.N)
+        assert self.ref_rows >= self.n_steps + self.N
         self.noise = self._dev(noise)[:self.n_steps].contiguous() if noise is not None else None
         assert self.noise is None or tuple(self.noise.shape) == (self.n_steps, B)
         self.p_ctrl = self._dev(p_ctrl, (2, B)) if p_ctrl is not None else None
@@ -66,8 +71,8 @@ class BatchedClosedLoop:
         """Advance `n_steps` control steps (default: the rest); one kernel launch per step."""
         n = self.n_steps - self.step if n_steps is None else int(n_steps)
         a = ClosedLoopArgs()
-        a.n_steps, a.first_step, a.ref_rows = n, self.step, int(self.ref.shape[0])
-        a.ref_shared, a.log_stride = int(self.ref.dim() == 2), self.n_steps
+        a.n_steps, a.first_step, a.ref_rows = n, self.step, self.ref_rows
+        a.ref_shared, a.log_stride = self.ref_layout, self.n_steps
         a.ref = self.ref.data_ptr()
         a.noise = self.noise.data_ptr() if self.noise is not None else None
         L = self._logs

@@ -545,7 +545,8 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     if (use_device(h)) return BNMPC_E_CUDA;
     LoopArgs la;
     memset(&la, 0, sizeof(la));
-    la.kind = h->ops->kind; la.ref_shared = a->ref_shared; la.log_stride = a->log_stride; la.batch = h->batch; la.Bp = h->Bp;
+    if (a->ref_shared < 0 || a->ref_shared > 2) return fail(BNMPC_E_ARG, "ref_shared must be 0 (batch-minor), 1 (shared) or 2 (instance-major)");
+    la.kind = h->ops->kind; la.ref_layout = a->ref_shared; la.ref_rows = a->ref_rows; la.log_stride = a->log_stride; la.batch = h->batch; la.Bp = h->Bp;
     la.ref = a->ref; la.noise = a->noise; la.Xsim = a->Xsim; la.U_plant = a->U_plant; la.U_ctrl = a->U_ctrl; la.a_log = a->a_log;
     la.status = a->status; la.qp_iter = a->qp_iter;
     la.xs = h->xs; la.acc = h->acc; la.cost = h->cost; la.abs_err = h->abs_err; la.p_plant = h->p_plant;

@@ -133,7 +133,9 @@ typedef struct bnmpc_closed_loop_args {
     int32_t n_steps;        /* control steps to run in this call */
     int32_t first_step;     /* index of the first step (row offset into ref, noise and the logs) */
     int32_t ref_rows;       /* rows of ref; needs first_step + n_steps + N <= ref_rows */
-    int32_t ref_shared;     /* 1: ref is one [rows][8] table for all instances, 0: [rows][8][batch] */
+    int32_t ref_shared;     /* layout of ref: 1 = one [rows][8] table shared by all instances, 0 = [rows][8][batch]
+                               (batch-minor), 2 = [batch][rows][8] (instance-major: a warp reads its window as one
+                               contiguous 2 KB segment - the layout to prefer for per-instance tables) */
     int32_t log_stride;     /* number of steps the log arrays were allocated for (>= first_step + n_steps) */
     int32_t reserved;
     const double* ref;      /* gen_circle_traj layout, 8 columns [px pz vx vz ax az+g 0 0] (src/generate_trajectory.py:7-28) */

@@ -63,7 +63,7 @@ static int solve_batch_t(const Opts* o, int B, const double* x0, const double* y
         sim.set(i, F_LBX, 0, x0 + (size_t)i * NX);
         sim.set(i, F_P, 0, p + (size_t)i * 2);
         const SmemPriv<M, T> ps;
-        Solver<M, T, HostGroup, SmemPriv<M, T>> sv(sim.sm.data(), *o, g, ps);
+        Solver<M, T, HostGroup, SmemPriv<M, T>> sv(sim.sm.data(), 0, *o, g, ps);
         api_solve<M, T>(sv, i, sim.gs);
         for (int k = 0; k <= N; k++) sim.get(i, F_X, k, x + ((size_t)i * (N + 1) + k) * NX);
         for (int k = 0; k < N; k++) sim.get(i, F_U, k, u + ((size_t)i * N + k) * NU);
@@ -93,10 +93,10 @@ static int closed_loop_t(const Opts* o, int kind, int B, int n_steps, int rows, 
     }
     for (int i = 0; i < B; i++) {
         const SmemPriv<M, T> ps;
-        Solver<M, T, HostGroup, SmemPriv<M, T>> sv(sim.sm.data(), *o, g, ps);
+        Solver<M, T, HostGroup, SmemPriv<M, T>> sv(sim.sm.data(), 0, *o, g, ps);
         for (int st = 0; st < n_steps; st++) {
             LoopArgs a{};
-            a.step = st; a.kind = kind; a.ref_shared = ref_shared; a.log_stride = n_steps; a.batch = B; a.Bp = Bp;
+            a.step = st; a.kind = kind; a.ref_layout = ref_shared; a.ref_rows = rows; a.log_stride = n_steps; a.batch = B; a.Bp = Bp;
             a.ref = ref; a.noise = noise; a.Xsim = Xsim; a.U_plant = U_plant; a.U_ctrl = U_ctrl; a.a_log = a_log;
             a.status = status; a.qp_iter = qp_iter; a.xs = xs.data(); a.acc = acc.data(); a.cost = cost; a.abs_err = abs_err;
             a.p_plant = pp.data();

@@ -26,9 +26,13 @@ def _gold_err(series, g, name):
     return float(np.max(np.abs(series[st[m]] - v[m])))
 
 
-def _run_loop(model, refs, x0, noise, pc, pp, S, **kw):
+def _run_loop(model, refs, x0, noise, pc, pp, S, layout='instance_major', **kw):
+    """refs [rows, 8] (shared table) or [B, rows, 8]; the latter is passed instance-major or batch-minor ([rows, 8, B])"""
     loop = pkg.BatchedClosedLoop(model, batch=x0.shape[0], device=0, **kw)
-    ref_t = torch.tensor(refs if refs.ndim == 2 else np.ascontiguousarray(np.transpose(refs, (1, 2, 0))))
+    if refs.ndim == 2 or layout == 'instance_major':
+        ref_t = torch.tensor(np.ascontiguousarray(refs))
+    else:
+        ref_t = torch.tensor(np.ascontiguousarray(np.transpose(refs, (1, 2, 0))))
     loop.init(torch.tensor(x0.T.copy()), ref_t, noise=None if noise is None else torch.tensor(noise),
               p_ctrl=torch.tensor(pc.T.copy()), p_plant=torch.tensor(pp.T.copy()), n_steps=S).run()
     r = {k: v.cpu().numpy() for k, v in loop.results().items()}
@@ -67,7 +71,7 @@ def test_closed_loop_matches_oracle(model):
     om = MODEL_ID[model]
     refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=5 + om, mass_sigma=0.05)
     want = co.closed_loop(co.default_opts(om), refs, x0, noise, pc, pp, S)
-    got, loop = _run_loop(model, refs, x0, noise, pc, pp, S)
+    got, loop = _run_loop(model, refs, x0, noise, pc, pp, S, layout='batch_minor' if model == 'jerk' else 'instance_major')
     assert np.array_equal(got['status'], want['status'])
     assert np.array_equal(got['qp_iter'], want['qp_iter'])
     for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):

@@ -30,7 +30,7 @@ def test_closed_loop_matches_oracle(model):
     refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=3 + model, mass_sigma=0.05)
     oo = co.default_opts(model)
     want = co.closed_loop(oo, refs, x0, noise, pc, pp, S)
-    got = hs.closed_loop(model, hs.FP64, hs.opts_from_oracle(oo), refs, x0, noise, pc, pp, S)
+    got = hs.closed_loop(model, hs.FP64, hs.opts_from_oracle(oo), refs, x0, noise, pc, pp, S, instance_major=(model == 0))
     assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
     for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
         np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-10, err_msg=k)
