@@ -90,15 +90,15 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': rs, 'samples': len(self.samples)}
 
 
-def make_inputs(lo, hi, n_steps, rows, device):
-    """BASELINE config 2 / SURVEY 8d inputs for the global instances lo..hi-1 (per-instance seeds keyed by the global id:
-    the numbers do not depend on how many ranks share the batch)."""
+def make_inputs(lo, hi, n_steps, rows, device, mass_sigma=0.0):
+    """BASELINE config 2 / 4 / SURVEY 8d inputs for the global instances lo..hi-1 (per-instance seeds keyed by the global
+    id: the numbers do not depend on how many ranks share the batch)."""
     from drone_attitude_control_b200.generate_trajectory import gen_circle_traj_batched
     from drone_attitude_control_b200.sharding import instance_inputs
-    inp = instance_inputs(lo, hi, n_steps)
+    inp = instance_inputs(lo, hi, n_steps, mass_sigma=mass_sigma)
     ref = gen_circle_traj_batched(500, rows - 500, inp['radius'], inp['center'], inp['phase'], device=device)      # [rows, 8, b]
     x0 = ref[0, :4, :].clone() + inp['dx0'].to(device)
-    return ref, x0, inp['noise'].to(device)
+    return ref, x0, inp['noise'].to(device), inp
 
 
 def run_ours(args):
@@ -118,10 +118,15 @@ def run_ours(args):
     B, K, W = args.batch, args.steps, args.warmup
     N = args.horizon
     rows = max(500 + N, W + K + N + 1)
-    ref, x0, noise = make_inputs(rank * B, (rank + 1) * B, W + K, rows, device=dev)       # weak scaling: B instances per rank
+    ref, x0, noise, inp = make_inputs(rank * B, (rank + 1) * B, W + K, rows, device=dev, mass_sigma=args.mass_sigma)   # weak scaling
     ref_im = ref.permute(2, 0, 1).contiguous()                                             # [B, rows, 8] instance-major
     loop = pkg.BatchedClosedLoop(args.model, batch=B, device=local, precision=args.precision, N_horizon=N, rti=args.rti)
-    loop.init(x0, ref_im, noise=noise, n_steps=W + K, log=True)
+    p_plant = None
+    if args.mass_sigma > 0:                                                                # BASELINE config 4: model mismatch
+        import torch as _t
+        p_plant = _t.stack([0.03277 * inp['mass_scale'], _t.full((B,), 9.81, dtype=_t.float64)])
+    ref_arg = pkg.CircleRef(inp['radius'], inp['center'], inp['phase'], n=rows - N) if args.ref == 'circle' else ref_im
+    loop.init(x0, ref_arg, noise=noise, p_plant=p_plant, n_steps=W + K, log=True)
     stream = torch.cuda.current_stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
 
@@ -234,7 +239,8 @@ def run_ours(args):
         'config': {'workload': f'{args.model}_model batched closed loop, {B} drones per GPU with randomised x0 and circle trajectories '
                                f'(BASELINE config 2), N_horizon {N}, {"SQP_RTI" if args.rti else "SQP to tol 1e-6"} + HPIPM-style IPM, '
                                f'noise sigma 0.01',
-                   'batch_per_gpu': B, 'horizon': N, 'model': args.model,
+                   'batch_per_gpu': B, 'horizon': N, 'model': args.model, 'plant_mass_sigma': args.mass_sigma,
+                   'reference': 'per-instance table [B, rows, 8] in HBM' if args.ref == 'table' else 'generated in the kernel (CircleRef)',
                    'l2': 'flushed between timed steps (256 MiB write, untimed)' if args.flush_l2 else 'not flushed',
                    'timing': 'sum of per-step CUDA-event durations on the launch stream, max over ranks'},
         'p50_step_latency_ms': float(np.median(step_ms)), 'p99_step_latency_ms': float(np.percentile(step_ms, 99)),
@@ -328,6 +334,8 @@ def main():
     ap.add_argument('--horizon', type=int, default=30)
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'])
     ap.add_argument('--rti', action='store_true')
+    ap.add_argument('--ref', default='table', choices=['table', 'circle'], help='trajectory table in HBM, or generated in the kernel')
+    ap.add_argument('--mass-sigma', type=float, default=0.0, help='BASELINE config 4: plant mass = 0.03277 (1 + N(0, sigma)) clipped to +-15 %%')
     ap.add_argument('--no-flush-l2', dest='flush_l2', action='store_false')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')

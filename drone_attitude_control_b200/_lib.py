@@ -71,6 +71,7 @@ def lib():
         'bnmpc_closed_loop_init': (C.c_int, [vp, dp, dp, dp]),
         'bnmpc_closed_loop_run': (C.c_int, [vp, C.POINTER(ClosedLoopArgs)]),
         'bnmpc_closed_loop_state': (C.c_int, [vp, dp, dp, dp, dp]),
+        'bnmpc_gen_circle_table': (C.c_int, [vp, dp, C.c_int, dp]),
         'bnmpc_launch_count': (C.c_int64, [vp]),
         'bnmpc_measure_fma_peak': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     }

@@ -17,6 +17,18 @@ from .params import ExperimentParameters
 p = ExperimentParameters()
 
 
+class CircleRef:
+    """Per-instance circle reference generated on the device (no table in HBM): gen_circle_traj of the reference
+    (src/generate_trajectory.py:7-28) with n samples per revolution; params [B, 4] = (radius, centre_x, centre_z, phase)."""
+
+    def __init__(self, radius, center, phase, n=500):
+        radius = torch.as_tensor(radius, dtype=torch.float64)
+        center = torch.as_tensor(center, dtype=torch.float64)
+        phase = torch.as_tensor(phase, dtype=torch.float64)
+        self.params = torch.stack([radius, center[:, 0], center[:, 1], phase], 1).contiguous()
+        self.n = int(n)
+
+
 class BatchedClosedLoop:
     def __init__(self, model='force', batch=1, device=0, precision='fp64', N_horizon=None, rti=False, **overrides):
         self.solver = BatchedAcadosOcpSolver(model, batch=batch, device=device, precision=precision,
@@ -35,20 +47,24 @@ class BatchedClosedLoop:
         return t
 
     def init(self, x0, ref, noise=None, p_ctrl=None, p_plant=None, n_steps=None, log=True):
-        """x0 [4, B]; ref [rows, 8] (one table shared by all drones), [rows, 8, B] (batch-minor) or [B, rows, 8]
-        (instance-major, preferred: a warp reads its window contiguously); noise [n_steps, B] or None; p_ctrl / p_plant
+        """x0 [4, B]; ref [rows, 8] (one table shared by all drones), [rows, 8, B] (batch-minor), [B, rows, 8]
+        (instance-major, preferred: a warp reads its window contiguously) or a CircleRef (no table); noise [n_steps, B] or None; p_ctrl / p_plant
         [2, B] or None (nominal mass 0.03277, g 9.81).  float64."""
         B = self.batch
         self.x0 = self._dev(x0, (4, B))
-        self.ref = self._dev(ref)
-        if self.ref.dim() == 2:
-            assert self.ref.shape[1] == 8
-            self.ref_layout, self.ref_rows = 1, int(self.ref.shape[0])
-        elif tuple(self.ref.shape[1:]) == (8, B):
-            self.ref_layout, self.ref_rows = 0, int(self.ref.shape[0])
+        if isinstance(ref, CircleRef):                      # generated on the fly from (radius, centre, phase)
+            self.ref = self._dev(ref.params, (B, 4))
+            self.ref_layout, self.ref_rows = 3, ref.n + self.N
         else:
-            assert self.ref.shape[0] == B and self.ref.shape[2] == 8, tuple(self.ref.shape)
-            self.ref_layout, self.ref_rows = 2, int(self.ref.shape[1])
+            self.ref = self._dev(ref)
+            if self.ref.dim() == 2:
+                assert self.ref.shape[1] == 8
+                self.ref_layout, self.ref_rows = 1, int(self.ref.shape[0])
+            elif tuple(self.ref.shape[1:]) == (8, B):
+                self.ref_layout, self.ref_rows = 0, int(self.ref.shape[0])
+            else:
+                assert self.ref.shape[0] == B and self.ref.shape[2] == 8, tuple(self.ref.shape)
+                self.ref_layout, self.ref_rows = 2, int(self.ref.shape[1])
         self.n_steps = int(n_steps if n_steps is not None else self.ref_rows - self.N)
         assert self.ref_rows >= self.n_steps + self.N
         self.noise = self._dev(noise)[:self.n_steps].contiguous() if noise is not None else None
@@ -66,6 +82,14 @@ class BatchedClosedLoop:
                               status=z(S, B, dt=torch.int32), qp_iter=z(S, B, dt=torch.int32))
             self._logs['Xsim'][0] = self.x0
         return self
+
+    def circle_table(self, rows=None):
+        """The table [B, rows, 8] the on-the-fly circle reference corresponds to (same device arithmetic)."""
+        assert self.ref_layout == 3
+        rows = self.ref_rows if rows is None else int(rows)
+        out = torch.empty((self.batch, rows, 8), dtype=torch.float64, device=self.device)
+        check(lib().bnmpc_gen_circle_table(self.solver.handle, C.c_void_p(self.ref.data_ptr()), rows, C.c_void_p(out.data_ptr())))
+        return out
 
     def run(self, n_steps=None):
         """Advance `n_steps` control steps (default: the rest); one kernel launch per step."""

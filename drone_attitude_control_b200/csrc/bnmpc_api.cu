@@ -165,6 +165,14 @@ __global__ void k_sim_step(int B, int ns, int nsub, double hstep, const double* 
     for (int j = 0; j < 4; j++) xn[(size_t)i * 4 + j] = xs[j] + e;
 }
 
+// gen_circle_traj for every instance, written instance-major [B][rows][8] with the arithmetic the solver uses on the fly
+__global__ void k_circle_table(int B, int rows, int n, const double* prm, double* out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * rows * 8) return;
+    const int col = (int)(idx % 8), row = (int)((idx / 8) % rows), inst = (int)(idx / ((size_t)rows * 8));
+    out[idx] = circle_ref(prm + (size_t)inst * 4, row, col, n);
+}
+
 __global__ void k_loop_init(int B, size_t Bp, const double* x0, const double* p_ctrl, const double* p_plant, double* xs, double* acc,
                             double* cost, double* abs_err, double* pp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -545,7 +553,8 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     if (use_device(h)) return BNMPC_E_CUDA;
     LoopArgs la;
     memset(&la, 0, sizeof(la));
-    if (a->ref_shared < 0 || a->ref_shared > 2) return fail(BNMPC_E_ARG, "ref_shared must be 0 (batch-minor), 1 (shared) or 2 (instance-major)");
+    if (a->ref_shared < 0 || a->ref_shared > 3) return fail(BNMPC_E_ARG, "ref_shared must be 0 (batch-minor), 1 (shared), 2 (instance-major) or 3 (circle parameters)");
+    if (a->ref_shared == 3 && a->ref_rows - h->cfg.horizon < 2) return fail(BNMPC_E_ARG, "circle reference needs ref_rows >= horizon + 2");
     la.kind = h->ops->kind; la.ref_layout = a->ref_shared; la.ref_rows = a->ref_rows; la.log_stride = a->log_stride; la.batch = h->batch; la.Bp = h->Bp;
     la.ref = a->ref; la.noise = a->noise; la.Xsim = a->Xsim; la.U_plant = a->U_plant; la.U_ctrl = a->U_ctrl; la.a_log = a->a_log;
     la.status = a->status; la.qp_iter = a->qp_iter;
@@ -556,6 +565,17 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
         if (int rc = next_queue(h, &q)) return rc;
         CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, q, h->stream)); h->launches++;
     }
+    return 0;
+}
+
+int bnmpc_gen_circle_table(void* handle, const double* params, int rows, double* table) {
+    Handle* h = (Handle*)handle;
+    if (!h || !params || !table) return fail(BNMPC_E_ARG, "NULL argument");
+    if (rows - h->cfg.horizon < 2) return fail(BNMPC_E_ARG, "rows must be >= horizon + 2");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const size_t tot = (size_t)h->batch * rows * 8;
+    k_circle_table<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->batch, rows, rows - h->cfg.horizon, params, table);
+    CK(cudaGetLastError()); h->launches++;
     return 0;
 }
 

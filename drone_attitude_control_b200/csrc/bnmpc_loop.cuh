@@ -12,7 +12,7 @@ namespace bnmpc {
 // field ids of the C-ABI (include/bnmpc.h)
 enum { F_X = 0, F_U = 1, F_YREF = 2, F_LBX = 3, F_UBX = 4, F_P = 5, F_PI = 6, F_LAM = 7 };
 enum { KIND_FORCE = 0, KIND_JERK = 1 };
-enum { REF_BATCH_MINOR = 0, REF_SHARED = 1, REF_INSTANCE_MAJOR = 2 };   // bnmpc_closed_loop_args.ref_shared
+enum { REF_BATCH_MINOR = 0, REF_SHARED = 1, REF_INSTANCE_MAJOR = 2, REF_CIRCLE = 3 };   // bnmpc_closed_loop_args.ref_shared
 
 // which block / local index holds global input g, state g
 template <class M> BN_HD constexpr int ublk(int g) { for (int b = 0; b < M::NBLK; b++) for (int j = 0; j < M::NUB; j++) if (M::ug(b, j) == g) return b; return 0; }
@@ -76,8 +76,9 @@ BN_HD void closed_loop_step(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs, 
     constexpr int n = M::NXB, m = M::NUB, NX = M::NX, NU = M::NU, NBLK = M::NBLK, NP = M::NP;
     const size_t Bp = a.Bp, Bt = (size_t)a.batch;
     YrefSrc ys;
-    ys.yref = nullptr; ys.ref = a.ref; ys.row0 = a.step;
-    if (a.ref_layout == REF_SHARED) { ys.ref_rs = 8; ys.ref_cs = 1; ys.ref_off = 0; }
+    ys.yref = nullptr; ys.ref = a.ref; ys.row0 = a.step; ys.circle_n = 0;
+    if (a.ref_layout == REF_CIRCLE) { ys.ref_rs = 0; ys.ref_cs = 0; ys.ref_off = (size_t)inst * 4; ys.circle_n = a.ref_rows - sv.N; }
+    else if (a.ref_layout == REF_SHARED) { ys.ref_rs = 8; ys.ref_cs = 1; ys.ref_off = 0; }
     else if (a.ref_layout == REF_INSTANCE_MAJOR) { ys.ref_rs = 8; ys.ref_cs = 1; ys.ref_off = (size_t)inst * a.ref_rows * 8; }
     else { ys.ref_rs = 8 * Bt; ys.ref_cs = Bt; ys.ref_off = (size_t)inst; }
     {
@@ -93,7 +94,10 @@ BN_HD void closed_loop_step(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs, 
     sv.template sqp_solve<T>(inst, gs, ys);
     // ---- leader lane of the instance: cost, converter, plant step, noise, logs ---------------------------------------
     if (sv.g.lane == 0) {
-        auto refv = [&](int row, int col) -> double { return a.ref[(size_t)row * ys.ref_rs + (size_t)col * ys.ref_cs + ys.ref_off]; };
+        auto refv = [&](int row, int col) -> double {
+            if (ys.circle_n > 0) return circle_ref(a.ref + ys.ref_off, row, col, ys.circle_n);
+            return a.ref[(size_t)row * ys.ref_rs + (size_t)col * ys.ref_cs + ys.ref_off];
+        };
         const int cost_stage = (a.kind == KIND_JERK) ? 1 : 0;   // controller.py:39 get(0,'x') / jerk controller.py:39 get(1,'x')
         double u0[NU], xo[4];
 #pragma unroll
@@ -150,7 +154,7 @@ template <class M, class T, class G, class PS>
 BN_HD void api_solve(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs) {
     constexpr int NX = M::NX, NU = M::NU, NP = M::NP;
     YrefSrc ys;
-    ys.ref = nullptr; ys.ref_rs = 0; ys.ref_cs = 0; ys.ref_off = 0; ys.row0 = 0;
+    ys.ref = nullptr; ys.ref_rs = 0; ys.ref_cs = 0; ys.ref_off = 0; ys.row0 = 0; ys.circle_n = 0;
     {
         ys.yref = gs.YREF + (size_t)inst * (gs.N + 1) * (NU + NX);
         T p[NP];

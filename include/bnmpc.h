@@ -135,7 +135,9 @@ typedef struct bnmpc_closed_loop_args {
     int32_t ref_rows;       /* rows of ref; needs first_step + n_steps + N <= ref_rows */
     int32_t ref_shared;     /* layout of ref: 1 = one [rows][8] table shared by all instances, 0 = [rows][8][batch]
                                (batch-minor), 2 = [batch][rows][8] (instance-major: a warp reads its window as one
-                               contiguous 2 KB segment - the layout to prefer for per-instance tables) */
+                               contiguous 2 KB segment - the layout to prefer for per-instance tables), 3 = no table:
+                               ref is [batch][4] = (radius, centre_x, centre_z, phase) of gen_circle_traj and every row
+                               is computed on the fly with n = ref_rows - horizon samples per revolution (T = 10 s) */
     int32_t log_stride;     /* number of steps the log arrays were allocated for (>= first_step + n_steps) */
     int32_t reserved;
     const double* ref;      /* gen_circle_traj layout, 8 columns [px pz vx vz ax az+g 0 0] (src/generate_trajectory.py:7-28) */
@@ -153,6 +155,10 @@ typedef struct bnmpc_closed_loop_args {
  * x0 [4][batch]; p_ctrl, p_plant [2][batch] (NULL = nominal mass 0.03277, g 9.81).  Device pointers. */
 int bnmpc_closed_loop_init(void* handle, const double* x0, const double* p_ctrl, const double* p_plant);
 int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* args);
+/* gen_circle_traj (src/generate_trajectory.py:7-28) for every instance from (radius, centre_x, centre_z, phase)
+ * [batch][4] with the device arithmetic of ref_shared = 3: table [batch][rows][8] (instance-major), rows = n + horizon.
+ * Device pointers. */
+int bnmpc_gen_circle_table(void* handle, const double* params, int rows, double* table);
 /* results so far: cost [batch] (closedLoopCost), abs_err [batch] (sum over steps of |pref-psim| over both position
  * coordinates = calc_aed numerator, src/store_results.py:233-236), x [4][batch] current plant state, acc [2][batch]
  * (jerk a_i).  Any pointer may be NULL.  Device pointers. */

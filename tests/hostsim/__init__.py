@@ -82,14 +82,24 @@ def solve_batch(model, prec, o, x0, yref, p, x=None, u=None):
     return dict(x=x, u=u, pi=pi, status=st, sqp_iter=si, qp_iter=qi)
 
 
-def closed_loop(model, prec, o, ref, x0, noise, p_ctrl, p_plant, n_steps, instance_major=False):
+def circle_table(params, rows, n):
+    params = np.ascontiguousarray(params, float)
+    out = np.zeros((params.shape[0], rows, 8))
+    lib().hs_circle_table(params.shape[0], rows, n, _dp(params), _dp(out))
+    return out
+
+
+def closed_loop(model, prec, o, ref, x0, noise, p_ctrl, p_plant, n_steps, instance_major=False, circle_rows=None):
     """ref [rows,8] shared or [B,rows,8]; x0 [B,4]; noise [n_steps,B]; p_* [B,2] (AoS like the oracle); converted to the
     layouts of the C-ABI (per-instance ref tables batch-minor [rows,8,B], or left instance-major).  Returns oracle-shaped
     arrays."""
     B = x0.shape[0]
-    shared = 1 if ref.ndim == 2 else (2 if instance_major else 0)
-    rows = ref.shape[-2]
-    refd = np.ascontiguousarray(ref if shared else np.transpose(ref, (1, 2, 0)), float)
+    if circle_rows is not None:                       # ref = circle parameters [B, 4], rows of the virtual table
+        shared, rows, refd = 3, int(circle_rows), np.ascontiguousarray(ref, float)
+    else:
+        shared = 1 if ref.ndim == 2 else (2 if instance_major else 0)
+        rows = ref.shape[-2]
+        refd = np.ascontiguousarray(ref if shared else np.transpose(ref, (1, 2, 0)), float)
     x0t = np.ascontiguousarray(x0.T, float)
     nz = None if noise is None else np.ascontiguousarray(noise, float)
     pc = np.ascontiguousarray(p_ctrl.T, float); pp = np.ascontiguousarray(p_plant.T, float)

@@ -121,6 +121,11 @@ static int closed_loop_t(const Opts* o, int kind, int B, int n_steps, int rows, 
 
 extern "C" {
 int hs_sizeof_opts(void) { return (int)sizeof(Opts); }
+// table [B][rows][8] of the on-the-fly circle reference (params [B][4]), n = samples per revolution
+void hs_circle_table(int B, int rows, int n, const double* prm, double* out) {
+    for (int i = 0; i < B; i++) for (int r = 0; r < rows; r++) for (int c = 0; c < 8; c++)
+        out[((size_t)i * rows + r) * 8 + c] = circle_ref(prm + (size_t)i * 4, r, c, n);
+}
 // AoS in/out like the C oracle's orc_solve_batch: x [B][N+1][NX], u [B][N][NU] (start iterate in, solution out)
 int hs_solve_batch(int model, int prec, const Opts* o, int B, const double* x0, const double* yref, const double* p, double* x,
                    double* u, double* pi, int* status, int* sqp_iter, int* qp_iter) {

@@ -35,3 +35,24 @@ def test_closed_loop_matches_oracle(model):
     for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
         np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-10, err_msg=k)
     np.testing.assert_allclose(got['cost'], want['cost'], rtol=1e-12)
+
+
+def test_on_the_fly_circle_reference():
+    """ref_shared = 3: the trajectory rows are computed in the kernel from (radius, centre, phase); same result as the
+    materialised table, which in turn is gen_circle_traj of the reference (src/generate_trajectory.py:7-28)."""
+    from oracle import nmpc_oracle as o
+    rng = np.random.default_rng(8)
+    B, S = 3, 12
+    prm = np.stack([rng.uniform(0.5, 1.0, B), rng.uniform(-0.15, 0.15, B), rng.uniform(-0.15, 0.15, B), rng.uniform(0, 6.28, B)], 1)
+    tab = hs.circle_table(prm, 530, 500)
+    for i in range(B):
+        want = o.gen_circle_traj(center=prm[i, 1:3], radius=prm[i, 0], phase=prm[i, 3])
+        np.testing.assert_allclose(tab[i], want, rtol=0, atol=5e-15)
+    np.testing.assert_array_equal(hs.circle_table(np.array([[1.0, 0, 0, 0]]), 530, 500)[0, 0], [1, 0, -0.0, 2 * np.pi / 10, -(2 * np.pi / 10) ** 2, 9.81, 0, 0])
+    x0 = tab[:, 0, :4] + rng.uniform(-0.05, 0.05, (B, 4)); noise = rng.normal(0, 0.01, (S, B))
+    p = np.repeat(np.array([[0.03277, 9.81]]), B, 0)
+    oo = hs.opts_from_oracle(co.default_opts(1))
+    a = hs.closed_loop(1, hs.FP64, oo, tab, x0, noise, p, p, S, instance_major=True)
+    b = hs.closed_loop(1, hs.FP64, oo, prm, x0, noise, p, p, S, circle_rows=530)
+    for k in ('Xsim', 'U_ctrl', 'cost', 'qp_iter', 'status'):
+        assert np.array_equal(a[k], b[k]), k
