@@ -124,6 +124,7 @@ typedef struct {
     double *qu, *qx, *zu, *zx, *ppi, *t_lbu, *t_ubu, *t_lbx, *t_ubx, *l_lbu, *l_ubu, *l_lbx, *l_ubx;
     double *dzu, *dzx, *dpi, *du_aff, *dx_aff;
     double *P, *pv, *Lr, *K;          /* Riccati factors */
+    double *Phi, *wv;                 /* closed-loop matrices A + B K (nx x nx per stage), w_k = gu + B'P rb */
     double *gu, *gx;                  /* modified gradients */
     double *rgu, *rgx, *rb;           /* residuals */
     int have_mult;
@@ -143,6 +144,7 @@ static inst_t *inst_new(int nx, int nu, int N) {
     s->l_lbu = dal(U); s->l_ubu = dal(U); s->l_lbx = dal(X); s->l_ubx = dal(X);
     s->dzu = dal(U); s->dzx = dal(X); s->dpi = dal(X); s->du_aff = dal(U); s->dx_aff = dal(X);
     s->P = dal((size_t)(N + 1) * nx * nx); s->pv = dal(X); s->Lr = dal((size_t)N * nu * nu); s->K = dal((size_t)N * nu * nx);
+    s->Phi = dal((size_t)N * nx * nx); s->wv = dal(U);
     s->gu = dal(U); s->gx = dal(X); s->rgu = dal(U); s->rgx = dal(X); s->rb = dal(X);
     return s;
 }
@@ -150,7 +152,7 @@ static inst_t *inst_new(int nx, int nu, int N) {
 static void inst_free(inst_t *s) {
     double **f[] = {&s->x, &s->u, &s->pi, &s->lam_lbu, &s->lam_ubu, &s->lam_lbx, &s->lam_ubx, &s->A, &s->B, &s->b, &s->qu, &s->qx,
                     &s->zu, &s->zx, &s->ppi, &s->t_lbu, &s->t_ubu, &s->t_lbx, &s->t_ubx, &s->l_lbu, &s->l_ubu, &s->l_lbx, &s->l_ubx,
-                    &s->dzu, &s->dzx, &s->dpi, &s->du_aff, &s->dx_aff, &s->P, &s->pv, &s->Lr, &s->K, &s->gu, &s->gx, &s->rgu, &s->rgx, &s->rb};
+                    &s->dzu, &s->dzx, &s->dpi, &s->du_aff, &s->dx_aff, &s->P, &s->pv, &s->Lr, &s->K, &s->gu, &s->gx, &s->rgu, &s->rgx, &s->rb, &s->Phi, &s->wv};
     for (size_t i = 0; i < sizeof(f) / sizeof(f[0]); i++) free(*f[i]);
     free(s);
 }
@@ -260,9 +262,12 @@ static void kkt_solve(const orc_opts *o, inst_t *s, int fact, int mode, double s
             Hx[j] = o->dt * o->w[j] + G1 + G2;
             gx[j] = s->rgx[i] + g1 - g2;
         }
-        /* Pb = P_{k+1} res_b_k + p_{k+1} */
-        double Pb[NXM];
-        for (int r = 0; r < nx; r++) { double a = pn[r]; for (int l = 0; l < nx; l++) a += Pn[r * nx + l] * s->rb[k * nx + l]; Pb[r] = a; }
+        /* The solve is written as a linear recurrence in p: p_k = c_k + Phi_k' p_{k+1} with Phi_k = A + B K_k, where
+         * everything that does not depend on p_{k+1} (Prb = P_{k+1} res_b_k, w = gu + B'Prb, c) is formed first; the
+         * feed-forward follows once p_{k+1} is known.  Same mathematics as r~ = gu + B'(P rb + p), p_k = gx + A'(P rb + p)
+         * + K'r~, re-associated so that the CUDA kernel can form Prb, w, c for all stages in parallel. */
+        double Prb[NXM];
+        for (int r = 0; r < nx; r++) { double a = 0; for (int l = 0; l < nx; l++) a += Pn[r * nx + l] * s->rb[k * nx + l]; Prb[r] = a; }
         double PA[NXM * NXM], PB[NXM * NUM];
         if (fact) {
             for (int r = 0; r < nx; r++) {
@@ -279,9 +284,10 @@ static void kkt_solve(const orc_opts *o, inst_t *s, int fact, int mode, double s
                 for (int r = c + 1; r < nu; r++) { double a = R[r * nu + c]; for (int l = 0; l < c; l++) a -= Lr[r * nu + l] * Lr[c * nu + l]; Lr[r * nu + c] = a / d; }
             }
         }
-        /* r~ = gu + B'Pb ; kff = -R~^{-1} r~ */
-        double rt[NUM];
-        for (int r = 0; r < nu; r++) { double a = gu[r]; for (int l = 0; l < nx; l++) a += B[l * nu + r] * Pb[l]; rt[r] = a; }
+        /* w = gu + B'Prb ; r~ = w + B'p_{k+1} ; kff = -R~^{-1} r~ */
+        double wv[NUM], rt[NUM];
+        for (int r = 0; r < nu; r++) { double a = gu[r]; for (int l = 0; l < nx; l++) a += B[l * nu + r] * Prb[l]; wv[r] = a; }
+        for (int r = 0; r < nu; r++) { double a = wv[r]; for (int l = 0; l < nx; l++) a += B[l * nu + r] * pn[l]; rt[r] = a; }
         double kff[NUM];
         for (int r = 0; r < nu; r++) { double a = -rt[r]; for (int l = 0; l < r; l++) a -= Lr[r * nu + l] * kff[l]; kff[r] = a / Lr[r * nu + r]; }
         for (int r = nu - 1; r >= 0; r--) { double a = kff[r]; for (int l = r + 1; l < nu; l++) a -= Lr[l * nu + r] * kff[l]; kff[r] = a / Lr[r * nu + r]; }
@@ -306,11 +312,16 @@ static void kkt_solve(const orc_opts *o, inst_t *s, int fact, int mode, double s
                     Pk[r * nx + c] = a;
                 }
                 for (int r = 0; r < nx; r++) for (int c = 0; c < r; c++) { double a = 0.5 * (Pk[r * nx + c] + Pk[c * nx + r]); Pk[r * nx + c] = Pk[c * nx + r] = a; }
+                /* Phi_k = A + B K */
+                double *Phi = s->Phi + (size_t)k * nx * nx;
+                for (int r = 0; r < nx; r++) for (int c = 0; c < nx; c++) { double a = A[r * nx + c]; for (int l = 0; l < nu; l++) a += B[r * nu + l] * K[l * nx + c]; Phi[r * nx + c] = a; }
             }
-            /* p_k = gx + A'Pb + K' r~   (S~'kff = -S~'R^{-1}r~ = K'r~) */
+            /* c = gx + A'Prb + K'w ; p_k = c + Phi_k' p_{k+1} */
+            const double *Phi = s->Phi + (size_t)k * nx * nx;
             for (int r = 0; r < nx; r++) {
-                double a = gx[r]; for (int l = 0; l < nx; l++) a += A[l * nx + r] * Pb[l];
-                for (int l = 0; l < nu; l++) a += K[l * nx + r] * rt[l];
+                double a = gx[r]; for (int l = 0; l < nx; l++) a += A[l * nx + r] * Prb[l];
+                for (int l = 0; l < nu; l++) a += K[l * nx + r] * wv[l];
+                for (int l = 0; l < nx; l++) a += Phi[l * nx + r] * pn[l];
                 s->pv[k * nx + r] = a;
             }
         }
@@ -320,11 +331,13 @@ static void kkt_solve(const orc_opts *o, inst_t *s, int fact, int mode, double s
     for (int k = 0; k < N; k++) {
         const double *A = s->A + (size_t)k * nx * nx, *B = s->B + (size_t)k * nx * nu, *K = s->K + (size_t)k * nu * nx;
         double du[NUM], dxn[NXM];
+        /* dx_{k+1} = e_k + Phi_k dx_k with e_k = res_b_k + B kff_k ; du_k = kff_k + K_k dx_k */
+        const double *Phi = s->Phi + (size_t)k * nx * nx;
         for (int r = 0; r < nu; r++) { double a = s->gu[k * nu + r]; if (k >= 1) for (int l = 0; l < nx; l++) a += K[r * nx + l] * dx[l]; du[r] = a; s->dzu[k * nu + r] = a; }
         for (int r = 0; r < nx; r++) {
             double a = s->rb[k * nx + r];
-            if (k >= 1) for (int l = 0; l < nx; l++) a += A[r * nx + l] * dx[l];
-            for (int l = 0; l < nu; l++) a += B[r * nu + l] * du[l];
+            for (int l = 0; l < nu; l++) a += B[r * nu + l] * s->gu[k * nu + l];
+            if (k >= 1) for (int l = 0; l < nx; l++) a += Phi[r * nx + l] * dx[l];
             dxn[r] = a;
         }
         const double *Pn = s->P + (size_t)(k + 1) * nx * nx, *pn = s->pv + (k + 1) * nx;
