@@ -7,7 +7,7 @@
 // during the solves; the CTA exists because of tensor memory:
 //
 //   * shared memory holds the part of an instance's working set that the Riccati sweeps and neighbouring stages touch
-//     (SmLayout<M,false>: 27 doubles per (stage, block) item for the force model, 13.4 KB per instance);
+//     (SmLayout<M,false>: 31 doubles per (stage, block) item for the force model, 15.4 KB per instance);
 //   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t: 15 doubles per item).  A warp
 //     owns the 32 TMEM lanes of its quarter; lane l keeps the records of its items in consecutive columns and moves a
 //     whole record with one tcgen05.ld / tcgen05.st (.32x32b.x32).  TMEM is used purely as a software-managed,
