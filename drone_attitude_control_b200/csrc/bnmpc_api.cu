@@ -315,17 +315,24 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return fail(BNMPC_E_CUDA, "no CUDA device: libbnmpc has no CPU path");
     if (device < 0 || device >= ndev) return fail(BNMPC_E_ARG, "device index out of range");
+    if (ops->smem_bytes(cfg->horizon) * BNMPC_WARPS_PER_CTA > 226 * 1024 || ops->tmem_cols(cfg->horizon) == 0)
+        return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of a CTA exceeds 227 KB of shared memory or 512 tensor-memory columns");
     CK(cudaSetDevice(device));
     Handle* h = new Handle();
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg; h->opts = make_opts(*cfg); h->ops = ops; h->batch = batch; h->device = device;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { delete h; return fail(BNMPC_E_CUDA, cudaGetErrorString(e)); }
+    // from here on every failure path releases the handle
+#define CKH(call)                                                                                                    \
+    do {                                                                                                             \
+        cudaError_t e_ = (call);                                                                                     \
+        if (e_ != cudaSuccess) {                                                                                     \
+            const std::string m_ = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+            bnmpc_destroy(h);                                                                                        \
+            return fail(BNMPC_E_CUDA, m_);                                                                           \
+        }                                                                                                            \
+    } while (0)
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     h->own_stream = true;
-    if (ops->smem_bytes(cfg->horizon) * BNMPC_WARPS_PER_CTA > 226 * 1024 || ops->tmem_cols(cfg->horizon) == 0) {
-        delete h;
-        return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of a CTA exceeds 227 KB of shared memory or 512 tensor-memory columns");
-    }
     const size_t SGd = ops->nu + ops->nx, Nn = cfg->horizon, es = ops->elem_size;
     h->nV = (Nn + 1) * SGd; h->nPI = Nn * ops->nx; h->nLAM = Nn * 2 * SGd;
     const size_t per = 2 * h->nV + h->nPI + h->nLAM + ops->nx + ops->np;
@@ -351,8 +358,8 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     {
         int per_sm = 0;
         cudaDeviceProp pr;
-        CK(cudaGetDeviceProperties(&pr, device));
-        CK(ops->max_ctas_per_sm(cfg->horizon, &per_sm));
+        CKH(cudaGetDeviceProperties(&pr, device));
+        CKH(ops->max_ctas_per_sm(cfg->horizon, &per_sm));
         if (per_sm < 1) { bnmpc_destroy(h); return fail(BNMPC_E_UNSUPPORTED, "kernel does not fit on an SM for this horizon"); }
         if (const char* e = getenv("BNMPC_CTAS_PER_SM")) {      // tuning knob: fewer resident CTAs per SM than would fit
             const int v = atoi(e);
@@ -361,17 +368,18 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
         const int want = (batch + BNMPC_WARPS_PER_CTA - 1) / BNMPC_WARPS_PER_CTA;
         h->ctas = want < per_sm * pr.multiProcessorCount ? want : per_sm * pr.multiProcessorCount;
     }
-    CK(cudaMemsetAsync(h->queue, 0, sizeof(int) * QUEUE_LEN, h->stream));
+    CKH(cudaMemsetAsync(h->queue, 0, sizeof(int) * QUEUE_LEN, h->stream));
     h->qi = 0;
-    CK(cudaMemsetAsync(h->gs_base, 0, h->gs_bytes, h->stream));
-    CK(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * batch, h->stream));
-    CK(cudaMemsetAsync(h->xs, 0, sizeof(double) * 11 * h->Bp, h->stream));
+    CKH(cudaMemsetAsync(h->gs_base, 0, h->gs_bytes, h->stream));
+    CKH(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * batch, h->stream));
+    CKH(cudaMemsetAsync(h->xs, 0, sizeof(double) * 11 * h->Bp, h->stream));
     // nominal parameters p = (mass, g) for every instance (reference src/params.py:37,42)
     double* pnom = nullptr;
     const double pn[2] = {0.03277, 9.81};
     { const double* d; int rc = stage_in(h, 0, pn, 2, 0, &d); if (rc) { bnmpc_destroy(h); return rc; } pnom = const_cast<double*>(d); }
-    CK(field_xfer(h, F_P, 0, pnom, ops->np, 0, 1));
-    CK(cudaStreamSynchronize(h->stream));
+    CKH(field_xfer(h, F_P, 0, pnom, ops->np, 0, 1));
+    CKH(cudaStreamSynchronize(h->stream));
+#undef CKH
     *handle = h;
     return 0;
 }

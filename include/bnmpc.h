@@ -76,7 +76,7 @@ typedef struct bnmpc_config {
     int32_t sqp_max_iter;   /* acados nlp_solver_max_iter default 100 (nlp_solver_type SQP, src/force_model/ocp.py:86) */
     int32_t qp_max_iter;    /* acados qp_solver_iter_max default 50 */
     int32_t rti;            /* 1: one QP per solve, no NLP residual test (SQP_RTI of the north-star) */
-    int32_t threads_per_block; /* 0 = library default */
+    int32_t threads_per_block; /* reserved (ignored): the launch shape is fixed, persistent CTAs of 4 warps */
     double dt;              /* interval length, tf / N (src/params.py:116, src/force_model/ocp.py:93) */
     double W[12];           /* diag of cost.W, order [x; u] (src/force_model/ocp.py:38-47) */
     double W_e[8];          /* diag of cost.W_e */
