@@ -269,3 +269,54 @@ def test_on_the_fly_circle_reference():
     b = loop2.init(x0, tab, noise=noise, n_steps=S).run().results()
     for k in ('Xsim', 'U_ctrl', 'cost', 'qp_iter', 'status'):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_acados_surface_fields_and_helpers():
+    """The rest of the AcadosOcpSolver surface: get of 'lam' / 'pi' / 'yref' / 'p', get_cost, solve_for_x0,
+    reset, get_stats('time_tot'), print_statistics, the B = 1 numpy facade."""
+    B = 16
+    oo = co.default_opts(0)
+    x0, yref = random_solve_inputs(0, B, seed=41, spread=0.1)
+    want = co.solve_batch(oo, x0, yref, np.repeat(P_NOM[None], B, 0))
+    s = pkg.BatchedAcadosOcpSolver('force', batch=B, device=0)
+    s.set_yref_all(yref)
+    u0 = s.solve_for_x0(torch.tensor(x0))
+    np.testing.assert_allclose(u0.cpu().numpy(), want['u'][:, 0], rtol=0, atol=1e-9)
+    N, nx, nu = s.N, s.nx, s.nu
+    U, X = N * nu, (N + 1) * nx
+    lam = want['lam']                       # oracle layout: lbu [N,nu] | ubu [N,nu] | lbx [N+1,nx] | ubx [N+1,nx]
+    lbu = lam[:, :U].reshape(B, N, nu); ubu = lam[:, U:2 * U].reshape(B, N, nu)
+    lbx = lam[:, 2 * U:2 * U + X].reshape(B, N + 1, nx); ubx = lam[:, 2 * U + X:].reshape(B, N + 1, nx)
+    np.testing.assert_allclose(s.get(0, 'lam').cpu().numpy(), np.hstack([lbu[:, 0], ubu[:, 0]]), rtol=0, atol=1e-9)
+    for k in (1, 7, N - 1):
+        np.testing.assert_allclose(s.get(k, 'lam').cpu().numpy(), np.hstack([lbu[:, k], lbx[:, k], ubu[:, k], ubx[:, k]]), rtol=0, atol=1e-9)
+    ny = nx + nu
+    np.testing.assert_array_equal(s.get(3, 'yref').cpu().numpy(), yref[:, 3 * ny:4 * ny])
+    np.testing.assert_array_equal(s.get(N, 'yref').cpu().numpy(), yref[:, N * ny:])
+    np.testing.assert_array_equal(s.get(0, 'p').cpu().numpy(), np.repeat(P_NOM[None], B, 0))
+    # get_cost: acados' objective at the iterate = sum dt/2 |y - yref|_W^2 + 1/2 |x_N - yref_N|_We^2
+    w = np.array([100, 100, 1, 1, 0.1, 0.1]); we = np.array([100, 100, 1, 1.0])
+    cost = np.zeros(B)
+    for k in range(N):
+        r = np.hstack([want['x'][:, k], want['u'][:, k]]) - yref[:, k * ny:(k + 1) * ny]
+        cost += 0.5 * 0.02 * (r * r * w).sum(1)
+    r = want['x'][:, N] - yref[:, N * ny:]
+    cost += 0.5 * (r * r * we).sum(1)
+    np.testing.assert_allclose(s.get_cost().cpu().numpy(), cost, rtol=1e-9)
+    assert s.get_stats('time_tot') > 0
+    s.print_statistics()
+    # reset() restores the state of a fresh solver: the same solve gives the same iteration counts again
+    qp1 = s.get_stats('qp_iter').cpu().numpy().copy()
+    s.reset(); s.set_yref_all(yref); s.solve_for_x0(torch.tensor(x0))
+    assert np.array_equal(s.get_stats('qp_iter').cpu().numpy(), qp1) and np.array_equal(qp1, want['qp_iter'])
+    # B = 1: numpy in, numpy out, int status - what the reference's follow_trajectory relies on
+    s1 = pkg.BatchedAcadosOcpSolver('force', batch=1, device=0)
+    for k in range(N):
+        s1.set(k, 'yref', yref[0, k * ny:(k + 1) * ny])
+    s1.set(N, 'yref', yref[0, N * ny:])
+    s1.set(0, 'lbx', x0[0]); s1.set(0, 'ubx', x0[0])
+    st = s1.solve()
+    assert isinstance(st, int) and st == 0
+    u = s1.get(0, 'u')
+    assert isinstance(u, np.ndarray) and u.shape == (nu,)
+    np.testing.assert_allclose(u, want['u'][0, 0], rtol=0, atol=1e-9)
