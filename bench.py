@@ -217,7 +217,7 @@ def run_ours(args):
         pass
     tf = C.c_double()
     _lib.check(_lib.lib().bnmpc_measure_fma_peak(local, _lib.FP32 if args.precision == 'fp32' else _lib.FP64, C.byref(tf)))
-    dims = dict(force=(2, 2, 1, 4, 2, 4), jerk=(2, 3, 1, 6, 2, 1), force_dense=(1, 4, 2, 4, 2, 4), jerk_dense=(1, 6, 2, 6, 2, 1))[args.model]
+    dims = dict(force=(2, 2, 1, 4, 2, 4), jerk=(2, 3, 1, 6, 2, 1), force_dense=(1, 4, 2, 4, 2, 4), thrust=(1, 4, 2, 4, 2, 4))[args.model]
     nblk, n, m, nx, nu, erk = dims
     qp_local = float(qp.sum())
     fl = flops_per_solve(nblk, n, m, N, erk, qp_local / (B * K)) * B                      # per launch, this rank
@@ -329,7 +329,7 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--model', default='force', choices=['force', 'jerk', 'force_dense'])
+    ap.add_argument('--model', default='force', choices=['force', 'jerk', 'force_dense', 'thrust'])
     ap.add_argument('--batch', type=int, default=4096, help='instances per GPU')
     ap.add_argument('--horizon', type=int, default=30)
     ap.add_argument('--precision', default='fp64', choices=['fp64', 'fp32'])

@@ -6,8 +6,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libbnmpc.so')
 
-MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE = 0, 1, 2
-MODELS = {'force': MODEL_FORCE, 'jerk': MODEL_JERK, 'force_dense': MODEL_FORCE_DENSE}
+MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_THRUST = 0, 1, 2, 3
+MODELS = {'force': MODEL_FORCE, 'jerk': MODEL_JERK, 'force_dense': MODEL_FORCE_DENSE, 'thrust': MODEL_THRUST}
 FP64, FP32 = 0, 1
 # acados return values (reference src/Readme.md:14-20)
 SUCCESS, FAILURE, MAXITER, MINSTEP, QP_FAILURE = 0, 1, 2, 3, 4

@@ -49,6 +49,7 @@ const ModelOps* pick_ops(int model, int precision) {
     case BNMPC_MODEL_FORCE: return ops_force(precision);
     case BNMPC_MODEL_JERK: return ops_jerk(precision);
     case BNMPC_MODEL_FORCE_DENSE: return ops_force_dense(precision);
+    case BNMPC_MODEL_THRUST: return ops_thrust(precision);
     }
     return nullptr;
 }
@@ -271,7 +272,7 @@ const char* bnmpc_last_error(void) { return g_err.c_str(); }
 
 int bnmpc_config_default(int model, bnmpc_config* c) {
     if (!c) return fail(BNMPC_E_ARG, "cfg is NULL");
-    if (model < 0 || model > BNMPC_MODEL_FORCE_DENSE) return fail(BNMPC_E_ARG, "unknown model");
+    if (model < 0 || model > BNMPC_MODEL_THRUST) return fail(BNMPC_E_ARG, "unknown model");
     memset(c, 0, sizeof(*c));
     const bool jerk = (model == BNMPC_MODEL_JERK);
     // reference src/params.py:37-61,113-122
@@ -298,6 +299,9 @@ int bnmpc_config_default(int model, bnmpc_config* c) {
         memcpy(c->lbx, lb, sizeof(lb)); memcpy(c->ubx, ub, sizeof(ub));
         c->lbu[0] = c->lbu[1] = -0.2 * GR; c->ubu[0] = c->ubu[1] = 1.3 * GR;
         c->sim_erk_stages = 4; c->sim_substeps = 1; c->sim_dt = c->dt;
+        if (model == BNMPC_MODEL_THRUST) {   // our nonlinear extension: u = (theta, Fd)
+            c->lbu[0] = -1.0; c->ubu[0] = 1.0; c->lbu[1] = 0.05; c->ubu[1] = 0.6;
+        }
     }
     return 0;
 }

@@ -259,5 +259,6 @@ struct OpsImpl {
 const ModelOps* ops_force(int precision);
 const ModelOps* ops_jerk(int precision);
 const ModelOps* ops_force_dense(int precision);
+const ModelOps* ops_thrust(int precision);
 
 }  // namespace bnmpc

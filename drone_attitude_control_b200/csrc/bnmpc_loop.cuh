@@ -11,7 +11,7 @@ namespace bnmpc {
 
 // field ids of the C-ABI (include/bnmpc.h)
 enum { F_X = 0, F_U = 1, F_YREF = 2, F_LBX = 3, F_UBX = 4, F_P = 5, F_PI = 6, F_LAM = 7 };
-enum { KIND_FORCE = 0, KIND_JERK = 1 };
+enum { KIND_FORCE = 0, KIND_JERK = 1, KIND_THRUST = 2 };
 enum { REF_BATCH_MINOR = 0, REF_SHARED = 1, REF_INSTANCE_MAJOR = 2, REF_CIRCLE = 3 };   // bnmpc_closed_loop_args.ref_shared
 
 // which block / local index holds global input g, state g
@@ -127,6 +127,10 @@ BN_HD void closed_loop_step(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs, 
             }
             a.acc[inst] = ai[0]; a.acc[Bp + inst] = ai[1];
             alog[0] = ai[0]; alog[1] = ai[1];
+        } else if (a.kind == KIND_THRUST) {               // the OCP input already is the plant input (theta, Fd)
+            up[0] = u0[0]; up[1] = u0[1];
+            for (int j = 0; j < sv.o.sim_substeps; j++) plant_step<double>(sv.o.sim_erk_stages, pp, sv.o.sim_dt, up, xs);
+            alog[0] = u0[1] * sin(u0[0]) / 0.03277; alog[1] = u0[1] * cos(u0[0]) / 0.03277;
         } else {
             up[0] = atan2(u0[0], u0[1]); up[1] = sqrt(u0[0] * u0[0] + u0[1] * u0[1]);     // dynamics.py:66-70
             for (int j = 0; j < sv.o.sim_substeps; j++) plant_step<double>(sv.o.sim_erk_stages, pp, sv.o.sim_dt, up, xs);

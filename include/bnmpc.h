@@ -33,6 +33,9 @@ extern "C" {
 #define BNMPC_MODEL_FORCE 0
 #define BNMPC_MODEL_JERK 1
 #define BNMPC_MODEL_FORCE_DENSE 2
+/* NOT in the reference: the plant model (src/plant.py:27-33, u = (theta, Fd)) as controller model - a nonlinear OCP that
+ * exercises the general path (sensitivities per stage and SQP iteration, several SQP iterations per solve). */
+#define BNMPC_MODEL_THRUST 3
 
 #define BNMPC_FP64 0
 #define BNMPC_FP32 1

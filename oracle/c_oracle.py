@@ -7,7 +7,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, '_build', 'libnmpc_oracle.so')
-MODEL_FORCE, MODEL_JERK = 0, 1
+MODEL_FORCE, MODEL_JERK, MODEL_THRUST = 0, 1, 2      # THRUST: the plant model as controller model (our nonlinear extension)
 NXM, NUM, NSM = 8, 4, 12
 
 

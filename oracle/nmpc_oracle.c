@@ -28,6 +28,8 @@
 #define NUM 4
 #define NSM (NXM + NUM)
 
+/* MODEL_PLANT doubles as the controller model of the "thrust" OCP (inputs theta, Fd: a nonlinear OCP that is not in the
+ * reference - it exercises the general SQP path: state/input dependent sensitivities, several SQP iterations) */
 enum { MODEL_FORCE = 0, MODEL_JERK = 1, MODEL_PLANT = 2 };
 
 typedef struct {
@@ -554,7 +556,14 @@ void orc_default_opts(int model, orc_opts *o) {
     for (int i = 0; i < 4; i++) { o->tol[i] = 1e-6; o->qp_tol[i] = 1e-6; }
     o->mu0 = 1.0; o->thr0 = 0.1; o->alpha_min = 1e-8; o->lam_min = 1e-16; o->t_min = 1e-16;
     const double wx[4] = {1e2, 1e2, 1.0, 1.0};
-    if (model == MODEL_JERK) {
+    if (model == MODEL_PLANT) {   /* thrust OCP (our extension): same state cost and boxes as the force model, u = (theta, Fd) */
+        o->erk_stages = 4;
+        for (int i = 0; i < 4; i++) { o->w[i] = wx[i]; o->w_e[i] = wx[i]; }
+        o->w[4] = o->w[5] = 1e-1;
+        const double lb[4] = {-1.2, -1.2, -1, -1}, ub[4] = {1.2, 1.2, 1, 1};
+        memcpy(o->lbx, lb, sizeof(lb)); memcpy(o->ubx, ub, sizeof(ub));
+        o->lbu[0] = -1.0; o->ubu[0] = 1.0; o->lbu[1] = 0.05; o->ubu[1] = 0.6;
+    } else if (model == MODEL_JERK) {
         o->erk_stages = 1;
         for (int i = 0; i < 4; i++) { o->w[i] = wx[i]; o->w_e[i] = wx[i]; }
         o->w[4] = o->w[5] = 0; o->w_e[4] = o->w_e[5] = 0; o->w[6] = o->w[7] = 1e-1;
@@ -690,6 +699,11 @@ static void closed_loop_one(void *vc, inst_t *s, double *yref, int i) {
             memcpy(xn, xs, sizeof(xs));
             for (int j = 0; j < 10; j++) erk_step(MODEL_PLANT, xn, up[j], pp, 1.0 / 500, 1, 1, xn, NULL);
             if (c->a_log) { c->a_log[o2] = ai[0]; c->a_log[o2 + 1] = ai[1]; }
+        } else if (o->model == MODEL_PLANT) {   /* thrust OCP: u0 already is the plant input */
+            nsub = 1;
+            up[0][0] = u0[0]; up[0][1] = u0[1];
+            erk_step(MODEL_PLANT, xs, up[0], pp, o->dt, 4, 1, xn, NULL);
+            if (c->a_log) { c->a_log[o2] = u0[1] * sin(u0[0]) / 0.03277; c->a_log[o2 + 1] = u0[1] * cos(u0[0]) / 0.03277; }
         } else {
             nsub = 1;
             up[0][0] = atan2(u0[0], u0[1]); up[0][1] = sqrt(u0[0] * u0[0] + u0[1] * u0[1]);

@@ -193,6 +193,15 @@ def jerk_ocp(N=N_HORIZON, **kw):
                    lbu=np.array([-JERK_LIM, -JERK_LIM]), ubu=np.array([JERK_LIM, JERK_LIM]), N=N, **kw)
 
 
+def thrust_ocp(N=N_HORIZON, **kw):
+    """NOT in the reference: the plant model (src/plant.py:27-33, inputs theta, Fd) used directly as controller model.
+    A nonlinear OCP that exercises the general SQP path (state/input dependent sensitivities, several SQP iterations)."""
+    return OcpSpec('thrust', 4, 2, f_plant, jac_plant, 4,
+                   w=np.array([1e2, 1e2, 1.0, 1.0, 1e-1, 1e-1]), w_e=np.array([1e2, 1e2, 1.0, 1.0]),
+                   lbx=np.array([-P_LIM, -P_LIM, -V_LIM, -V_LIM]), ubx=np.array([P_LIM, P_LIM, V_LIM, V_LIM]),
+                   lbu=np.array([-1.0, 0.05]), ubu=np.array([1.0, 0.6]), N=N, **kw)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # HPIPM-style IPM on the stage-structured QP, dense KKT solves
 # ----------------------------------------------------------------------------------------------------------------------

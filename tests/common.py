@@ -38,3 +38,23 @@ def random_loop_inputs(B, S, seed, N=30, mass_sigma=0.0):
     if mass_sigma > 0:
         p_plant[:, 0] *= 1 + np.clip(rng.normal(0, mass_sigma, B), -0.15, 0.15)
     return refs, x0, noise, p_ctrl, p_plant
+
+
+def thrust_refs(refs):
+    """Reference tables for the thrust OCP (u = (theta, Fd)): columns 4, 5 hold the input reference (0, m g)."""
+    r = np.array(refs, float)
+    r[..., 4] = 0.0
+    r[..., 5] = o.GRAVITY
+    return r
+
+
+def thrust_solve_inputs(B, seed, spread=0.08, N=30):
+    rng = np.random.default_rng(seed)
+    x0s, yrefs = [], []
+    for _ in range(B):
+        ref = thrust_refs(o.gen_circle_traj(n_horizon=max(N, 30), radius=rng.uniform(0.5, 1.0), center=rng.uniform(-0.15, 0.15, 2),
+                                            phase=rng.uniform(0, 2 * np.pi)))
+        st = int(rng.integers(0, 400))
+        x0s.append(ref[st, :4] + rng.uniform(-spread, spread, 4))
+        yrefs.append(np.hstack([ref[st:st + N, :6].ravel(), ref[st + N, :4]]))
+    return np.array(x0s), np.array(yrefs)

@@ -12,7 +12,7 @@ _SRC = [os.path.join(_HERE, 'hostsim.cpp')] + [
     os.path.join(_HERE, '..', '..', 'drone_attitude_control_b200', 'csrc', f)
     for f in ('bnmpc_core.cuh', 'bnmpc_loop.cuh', 'generated/models_gen.cuh')]
 
-MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_JERK_DENSE = 0, 1, 2, 3
+MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_JERK_DENSE, MODEL_THRUST = 0, 1, 2, 3, 4
 FP64, FP32 = 0, 1
 
 
@@ -47,7 +47,7 @@ def lib():
 def opts_from_oracle(oo):
     """oracle.c_oracle.Opts -> product Opts (same numbers the C-ABI's bnmpc_config_default produces)."""
     o = Opts()
-    jerk = oo.model == 1
+    jerk = oo.model == 1        # (oracle model 2 = thrust: force-like integrator settings)
     o.N, o.erk_stages, o.sqp_max_iter, o.qp_max_iter, o.rti = oo.N, oo.erk_stages, oo.sqp_max_iter, oo.qp_max_iter, oo.rti
     o.sim_erk_stages, o.sim_substeps = (1, 10) if jerk else (4, 1)
     o.dt, o.sim_dt = oo.dt, (1.0 / 500 if jerk else oo.dt)

@@ -116,6 +116,8 @@ static int closed_loop_t(const Opts* o, int kind, int B, int n_steps, int rows, 
     case 5: return fn<Model_force_dense, float>(__VA_ARGS__);                              \
     case 6: return fn<Model_jerk_dense, double>(__VA_ARGS__);                              \
     case 7: return fn<Model_jerk_dense, float>(__VA_ARGS__);                               \
+    case 8: return fn<Model_plant, double>(__VA_ARGS__);                                   \
+    case 9: return fn<Model_plant, float>(__VA_ARGS__);                                    \
     }                                                                                      \
     return -2;
 
@@ -135,7 +137,7 @@ int hs_solve_batch(int model, int prec, const Opts* o, int B, const double* x0, 
 int hs_closed_loop(int model, int prec, const Opts* o, int B, int n_steps, int rows, const double* ref, int ref_shared,
                    const double* x0, const double* noise, const double* p_ctrl, const double* p_plant, double* Xsim, double* U_plant,
                    double* U_ctrl, double* a_log, double* cost, double* abs_err, int* status, int* qp_iter) {
-    const int kind = (model == 1 || model == 3) ? KIND_JERK : KIND_FORCE;
+    const int kind = (model == 1 || model == 3) ? KIND_JERK : (model == 4 ? KIND_THRUST : KIND_FORCE);
     DISPATCH(closed_loop_t, model, prec, o, kind, B, n_steps, rows, ref, ref_shared, x0, noise, p_ctrl, p_plant, Xsim, U_plant, U_ctrl,
              a_log, cost, abs_err, status, qp_iter)
 }

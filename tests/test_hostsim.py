@@ -56,3 +56,25 @@ def test_on_the_fly_circle_reference():
     b = hs.closed_loop(1, hs.FP64, oo, prm, x0, noise, p, p, S, circle_rows=530)
     for k in ('Xsim', 'U_ctrl', 'cost', 'qp_iter', 'status'):
         assert np.array_equal(a[k], b[k]), k
+
+
+def test_nonlinear_thrust_ocp_matches_oracle():
+    """General path of the product templates (one block, sensitivities stored per stage, several SQP iterations)."""
+    from common import thrust_refs, thrust_solve_inputs
+    oo = co.default_opts(co.MODEL_THRUST)
+    x0, yref = thrust_solve_inputs(3, seed=5)
+    p = np.repeat(np.array([[0.03277, 9.81]]), 3, 0)
+    want = co.solve_batch(oo, x0, yref, p)
+    got = hs.solve_batch(hs.MODEL_THRUST, hs.FP64, hs.opts_from_oracle(oo), x0, yref, p)
+    assert np.array_equal(got['status'], want['status']) and np.array_equal(got['sqp_iter'], want['sqp_iter'])
+    assert np.array_equal(got['qp_iter'], want['qp_iter']) and want['sqp_iter'].min() >= 2
+    np.testing.assert_allclose(got['u'], want['u'], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(got['x'], want['x'], rtol=0, atol=1e-10)
+    S, B = 10, 2
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=9, mass_sigma=0.05)
+    refs = thrust_refs(refs)
+    want = co.closed_loop(oo, refs, x0, noise, pc, pp, S)
+    got = hs.closed_loop(hs.MODEL_THRUST, hs.FP64, hs.opts_from_oracle(oo), refs, x0, noise, pc, pp, S, instance_major=True)
+    assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
+    for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
+        np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-10, err_msg=k)

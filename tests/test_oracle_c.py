@@ -73,3 +73,24 @@ def test_threads_do_not_change_results():
     a = co.closed_loop(co.default_opts(co.MODEL_FORCE), ref, x0, noise, pp, pp, 20, nthreads=1)
     b = co.closed_loop(co.default_opts(co.MODEL_FORCE), ref, x0, noise, pp, pp, 20, nthreads=4)
     assert np.array_equal(a['Xsim'], b['Xsim']) and np.array_equal(a['qp_iter'], b['qp_iter'])
+
+
+def test_c_vs_numpy_nonlinear_thrust_ocp():
+    """The thrust OCP (plant model as controller model, not in the reference) exercises the general SQP path: several
+    SQP iterations, sensitivities that change with the iterate.  The two oracles must agree there too."""
+    from common import thrust_solve_inputs
+    B = 4
+    x0s, yrefs = thrust_solve_inputs(B, seed=3)
+    rc = co.solve_batch(co.default_opts(co.MODEL_THRUST), x0s, yrefs, np.repeat(P, B, 0))
+    assert rc['sqp_iter'].min() >= 2
+    spec = o.thrust_ocp()
+    for i in range(B):
+        sol = o.OracleOcpSolver(spec)
+        for k in range(30):
+            sol.set(k, 'yref', yrefs[i, k * 6:(k + 1) * 6])
+        sol.set(30, 'yref', yrefs[i, 180:])
+        sol.set(0, 'lbx', x0s[i])
+        assert sol.solve() == rc['status'][i]
+        assert sol.sqp_iter == rc['sqp_iter'][i] and sol.qp_iter == rc['qp_iter'][i]
+        np.testing.assert_allclose(rc['u'][i], sol.u, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(rc['x'][i], sol.x, rtol=0, atol=1e-9)
