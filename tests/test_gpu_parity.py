@@ -351,3 +351,20 @@ def test_nonlinear_thrust_ocp_matches_oracle():
     tight = dev <= 1e-9
     for k in ('U_ctrl', 'U_plant', 'a'):
         np.testing.assert_allclose(got[k][tight], want[k][tight], rtol=0, atol=1e-9, err_msg=k)
+
+
+@pytest.mark.parametrize('model', ['force', 'jerk'])
+def test_odd_shapes(model):
+    """Batch sizes around the warp / CTA / grid boundaries and tiny or odd horizons (edge cases of the launch shape:
+    4 instances per CTA, work queue, 32-lane rounds over (N+1)*2 items, tensor-memory columns per round)."""
+    om = MODEL_ID[model]
+    for B, N in ((1, 30), (3, 30), (5, 1), (7, 2), (33, 3), (130, 15), (131, 16), (257, 31), (64, 47)):
+        x0, yref = random_solve_inputs(om, B, seed=100 + B + N, N=N)
+        want = co.solve_batch(co.default_opts(om, N=N), x0, yref, np.repeat(P_NOM[None], B, 0))
+        s = pkg.BatchedAcadosOcpSolver(model, batch=B, device=0, N_horizon=N, numpy_io=False)
+        s.set_yref_all(yref); s.set(0, 'lbx', x0); s.set(0, 'ubx', x0)
+        st = s.solve()
+        assert np.array_equal(torch.as_tensor(st).cpu().numpy().reshape(-1), want['status']), (B, N)
+        assert np.array_equal(s.get_stats('qp_iter').cpu().numpy(), want['qp_iter']), (B, N)
+        np.testing.assert_allclose(s.get(0, 'u').cpu().numpy(), want['u'][:, 0], rtol=0, atol=1e-9, err_msg=str((B, N)))
+        np.testing.assert_allclose(s.get(N, 'x').cpu().numpy(), want['x'][:, N], rtol=0, atol=1e-9, err_msg=str((B, N)))
