@@ -239,7 +239,7 @@ def run_ours(args):
         'config': {'workload': f'{args.model}_model batched closed loop, {B} drones per GPU with randomised x0 and circle trajectories '
                                f'(BASELINE config 2), N_horizon {N}, {"SQP_RTI" if args.rti else "SQP to tol 1e-6"} + HPIPM-style IPM, '
                                f'noise sigma 0.01',
-                   'batch_per_gpu': B, 'horizon': N, 'model': args.model, 'plant_mass_sigma': args.mass_sigma,
+                   'batch_per_gpu': B, 'horizon': N, 'controller': args.model, 'plant_mass_sigma': args.mass_sigma,
                    'reference': 'per-instance table [B, rows, 8] in HBM' if args.ref == 'table' else 'generated in the kernel (CircleRef)',
                    'l2': 'flushed between timed steps (256 MiB write, untimed)' if args.flush_l2 else 'not flushed',
                    'timing': 'sum of per-step CUDA-event durations on the launch stream, max over ranks'},
@@ -317,7 +317,7 @@ def run_reference(args):
         'ms_per_step': dt / K * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': f'{args.model}_model batched closed loop (BASELINE config 2), N_horizon {args.horizon}; CPU restatement of the '
                                f'reference path (acados is not installable here), bounded sample', 'batch_per_gpu': args.batch,
-                   'horizon': args.horizon, 'model': args.model},
+                   'horizon': args.horizon, 'controller': args.model},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))

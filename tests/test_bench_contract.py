@@ -18,7 +18,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d['value'] > 0 and d['e2e']['value'] == d['value'] and d['e2e']['h2d_bytes_per_step'] == 0
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
-    assert d['config']['model'] == 'force' and d['config']['horizon'] == 30 and d['vs_baseline'] is None
+    assert d['config']['controller'] == 'force' and d['config']['horizon'] == 30 and d['vs_baseline'] is None
+    assert 'workload' in d['config'] and 'model' not in d['config']
 
 
 def test_flop_and_byte_model_matches_design():
