@@ -165,15 +165,37 @@ class BatchedAcadosOcpSolver:
         print('bnmpc statistics: instances %d | status histogram %s | sqp_iter max %d | qp_iter min/mean/max %d/%.1f/%d' % (
             self.batch, np.bincount(st, minlength=5).tolist(), si.max(), qi.min(), qi.mean(), qi.max()))
 
-    def solve_for_x0(self, x0_bar):
-        """acados convenience used by the reference's dev scripts (src/force_model/ocp.py:162-164)."""
-        self.set(0, 'lbx', x0_bar)
-        self.set(0, 'ubx', x0_bar)
-        status = self.solve()
-        bad = (status != 0) if isinstance(status, int) else bool((torch.as_tensor(status) != 0).any())
-        if bad:
-            raise BnmpcError(f'solver returned status {status}')
-        return self.get(0, 'u')
+    def solve_for_x0(self, x0_bar, fail_on_nonzero_status=True):
+        """acados' solve_for_x0 (used by the reference's dev scripts, src/force_model/ocp.py:162-164): embed x0, solve, return
+        u0 - one library call (one kernel launch in FP64).  Raises on a non-zero status like acados does, unless
+        fail_on_nonzero_status=False (then the statuses are available through get_stats('status'))."""
+        keep, ptr, on_dev = self._as_arg(x0_bar, self.nx)
+        if on_dev:
+            u0 = torch.empty((self.batch, self.nu), dtype=torch.float64, device=self.device)
+            st = torch.empty(self.batch, dtype=torch.int32, device=self.device)
+            up, sp = C.c_void_p(u0.data_ptr()), C.c_void_p(st.data_ptr())
+        else:
+            u0 = np.empty((self.batch, self.nu)); st = np.empty(self.batch, np.int32)
+            up, sp = C.c_void_p(u0.ctypes.data), C.c_void_p(st.ctypes.data)
+        ev0 = torch.cuda.Event(enable_timing=True); ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record(self._stream)
+        check(lib().bnmpc_solve_for_x0(self._h, ptr, up, sp, on_dev))
+        ev1.record(self._stream)
+        self._ev = (ev0, ev1)
+        self._keep = keep
+        if fail_on_nonzero_status:
+            bad = bool((st != 0).any())
+            if bad:
+                raise BnmpcError(f'solver returned status {st}')
+        if not on_dev and self.numpy_io:
+            return u0[0] if self.batch == 1 else u0
+        return u0 if on_dev else torch.from_numpy(u0).to(self.device)
+
+    def solve_for_x0_into(self, x0_host, u0_host, status_host):
+        """Zero-allocation form for tight loops: pinned host tensors in and out (x0 [B, nx], u0 [B, nu] float64,
+        status [B] int32); returns when the results are in host memory."""
+        check(lib().bnmpc_solve_for_x0(self._h, C.c_void_p(x0_host.data_ptr()), C.c_void_p(u0_host.data_ptr()),
+                                       C.c_void_p(status_host.data_ptr()), 0))
 
     def get_cost(self):
         """acados get_cost(): the NLP objective at the current iterate (LINEAR_LS, stage cost scaled by dt)."""

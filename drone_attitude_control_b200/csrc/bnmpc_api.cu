@@ -34,7 +34,7 @@ struct Handle {
     bool own_stream;
     GsAny gs;                      // persistent per-instance state in HBM
     char* gs_base;
-    size_t gs_bytes, nV, nPI, nLAM;   // elements per instance
+    size_t gs_bytes, nV, nPI, nLAM, nYREF;   // elements per instance
     int32_t* ints;                 // status | sqp_iter | qp_iter | have_mult
     double* stage[4];              // device staging buffers for host<->device AoS copies
     size_t stage_cap[4];
@@ -339,13 +339,15 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     h->own_stream = true;
     const size_t SGd = ops->nu + ops->nx, Nn = cfg->horizon, es = ops->elem_size;
     h->nV = (Nn + 1) * SGd; h->nPI = Nn * ops->nx; h->nLAM = Nn * 2 * SGd;
-    const size_t per = 2 * h->nV + h->nPI + h->nLAM + ops->nx + ops->np;
+    h->nYREF = Nn * SGd + ops->nx;
+    const size_t per = h->nV + h->nYREF + h->nPI + h->nLAM + ops->nx + ops->np;
     h->gs_bytes = per * batch * es;
     h->Bp = ((size_t)batch + 31) / 32 * 32;
     bool ok = cudaMalloc(&h->gs_base, h->gs_bytes) == cudaSuccess;
     ok = ok && cudaMalloc(&h->ints, sizeof(int32_t) * 4 * batch) == cudaSuccess;
     ok = ok && cudaMalloc(&h->queue, sizeof(int) * QUEUE_LEN) == cudaSuccess;
     ok = ok && cudaMalloc(&h->xs, sizeof(double) * 11 * h->Bp) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->gs.U0, sizeof(double) * (size_t)batch * ops->nu) == cudaSuccess;
     if (!ok) {
         const std::string msg = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
         bnmpc_destroy(h);
@@ -355,7 +357,7 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     {
         char* p = h->gs_base;
         h->gs.V = p; p += h->nV * batch * es; h->gs.PI = p; p += h->nPI * batch * es; h->gs.LAM = p; p += h->nLAM * batch * es;
-        h->gs.YREF = p; p += h->nV * batch * es; h->gs.X0 = p; p += (size_t)ops->nx * batch * es; h->gs.PAR = p;
+        h->gs.YREF = p; p += h->nYREF * batch * es; h->gs.X0 = p; p += (size_t)ops->nx * batch * es; h->gs.PAR = p;
     }
     h->gs.status = h->ints; h->gs.sqp_iter = h->ints + batch; h->gs.qp_iter = h->ints + 2 * batch; h->gs.have_mult = h->ints + 3 * batch;
     h->gs.B = batch; h->gs.N = cfg->horizon;
@@ -397,6 +399,7 @@ int bnmpc_destroy(void* handle) {
     if (h->ints) cudaFree(h->ints);
     if (h->queue) cudaFree(h->queue);
     if (h->xs) cudaFree(h->xs);
+    if (h->gs.U0) cudaFree(h->gs.U0);
     for (int i = 0; i < 4; i++) if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -467,6 +470,10 @@ int bnmpc_set_yref_all(void* handle, const double* value, int on_device) {
     if (use_device(h)) return BNMPC_E_CUDA;
     const int N = h->cfg.horizon;
     const size_t per = (size_t)N * (h->ops->nx + h->ops->nu) + h->ops->nx;
+    if (h->ops->elem_size == 8) {   // the state keeps yref in exactly this layout: a plain copy, no kernel
+        CK(cudaMemcpyAsync(h->gs.YREF, value, per * h->batch * sizeof(double), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
     const double* d;
     if (int rc = stage_in(h, 2, value, per * h->batch, on_device, &d)) return rc;
     {
@@ -493,6 +500,29 @@ int bnmpc_solve(void* handle) {
     int* q;
     if (int rc = next_queue(h, &q)) return rc;
     CK(h->ops->solve(h->gs, h->opts, h->ctas, q, h->stream)); h->launches++;
+    return 0;
+}
+
+int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* status, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !x0) return fail(BNMPC_E_ARG, "NULL argument");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const int B = h->batch, nx = h->ops->nx, nu = h->ops->nu;
+    const cudaMemcpyKind in = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind out = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (h->ops->elem_size == 8) {
+        CK(cudaMemcpyAsync(h->gs.X0, x0, sizeof(double) * B * nx, in, h->stream));            // lbx_0 = ubx_0 = x0_bar
+    } else {
+        const double* d;
+        if (int rc = stage_in(h, 0, x0, (size_t)B * nx, on_device, &d)) return rc;
+        CK(field_xfer(h, F_LBX, 0, const_cast<double*>(d), nx, nx, 1));
+    }
+    int* q;
+    if (int rc = next_queue(h, &q)) return rc;
+    CK(h->ops->solve(h->gs, h->opts, h->ctas, q, h->stream)); h->launches++;
+    if (u0) CK(cudaMemcpyAsync(u0, h->gs.U0, sizeof(double) * B * nu, out, h->stream));   // gathered by the solve kernel
+    if (status) CK(cudaMemcpyAsync(status, h->gs.status, sizeof(int32_t) * B, out, h->stream));
+    if (!on_device) CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

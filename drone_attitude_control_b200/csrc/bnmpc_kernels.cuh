@@ -32,6 +32,7 @@ namespace bnmpc {
 struct GsAny {
     void *V, *PI, *LAM, *YREF, *X0, *PAR;
     int32_t *status, *sqp_iter, *qp_iter, *have_mult;
+    double* U0;
     int B, N;
 };
 template <class T> inline Gs<T> gs_cast(const GsAny& a) {

@@ -41,8 +41,8 @@ BN_HD T* field_ptr(const Gs<T>& gs, int NX, int NU, int NP, int inst, int field,
     switch (field) {
     case F_X: return gs.V + (size_t)inst * (N + 1) * SG + k * SG + NU + j;
     case F_U: return gs.V + (size_t)inst * (N + 1) * SG + k * SG + j;
-    case F_YREF:   // acados order [x-part; u-part] (Vx = [I; 0], Vu = [0; I]); stored [u-part; x-part]
-        return gs.YREF + (size_t)inst * (N + 1) * SG + k * SG + (j < NX ? NU + j : j - NX);
+    case F_YREF:   // acados order [x-part; u-part] (Vx = [I; 0], Vu = [0; I]), stored as is
+        return gs.YREF + (size_t)inst * (N * SG + NX) + k * SG + j;
     case F_LBX: case F_UBX: return gs.X0 + (size_t)inst * NX + j;
     case F_P: return gs.PAR + (size_t)inst * NP + j;
     case F_PI: return gs.PI + (size_t)inst * N * NX + k * NX + j;
@@ -160,7 +160,7 @@ BN_HD void api_solve(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs) {
     YrefSrc ys;
     ys.ref = nullptr; ys.ref_rs = 0; ys.ref_cs = 0; ys.ref_off = 0; ys.row0 = 0; ys.circle_n = 0;
     {
-        ys.yref = gs.YREF + (size_t)inst * (gs.N + 1) * (NU + NX);
+        ys.yref = gs.YREF + (size_t)inst * (gs.N * (NU + NX) + NX);
         T p[NP];
 #pragma unroll
         for (int j = 0; j < NP; j++) p[j] = gs.PAR[(size_t)inst * NP + j];
@@ -169,6 +169,12 @@ BN_HD void api_solve(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs) {
     }
     sv.g.sync();
     sv.template sqp_solve<T>(inst, gs, ys);
+    if (sv.g.lane == 0) {      // ocp_solver.get(0, 'u') for free: the solution is still in shared memory
+        using SL = typename Solver<M, T, G, PS>::SL;
+#pragma unroll
+        for (int gi = 0; gi < NU; gi++) gs.U0[(size_t)inst * NU + gi] = double(sv.S(SL::VAL + uloc<M>(gi), ublk<M>(gi)));
+    }
+    sv.g.sync();
 }
 
 }  // namespace bnmpc

@@ -119,6 +119,11 @@ int bnmpc_reset(void* handle);
 /* ocp_solver.solve() (src/force_model/controller.py:32): one acados-style SQP run per instance from the stored
  * iterate with the stored x0 / yref / p.  Per-instance status via bnmpc_get_stats. */
 int bnmpc_solve(void* handle);
+/* ocp_solver.solve_for_x0(x0_bar) of acados_template (used by the reference's dev scripts, src/force_model/ocp.py:162-164)
+ * = set(0,'lbx',x0); set(0,'ubx',x0); solve(); get(0,'u'), for all instances in ONE call: x0 AoS [batch][nx] in,
+ * u0 AoS [batch][nu] and status int32 [batch] out (either may be NULL).  In FP64 the inputs are copied straight into the
+ * solver state and the outputs straight out of it: one kernel launch per call. */
+int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* status, int on_device);
 /* ocp_solver.get_stats / status: int32 [batch] */
 int bnmpc_get_stats(void* handle, int which, int32_t* out, int on_device);
 

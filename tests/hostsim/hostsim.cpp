@@ -27,16 +27,18 @@ struct HostGroup {
 
 template <class M, class T>
 struct Sim {
-    Gs<T> gs; std::vector<T> buf, sm; std::vector<int32_t> ints; int B, N;
+    Gs<T> gs; std::vector<T> buf, sm; std::vector<int32_t> ints; std::vector<double> u0; int B, N;
     Sim(int B_, int N_) : B(B_), N(N_) {
         constexpr int SG = M::NU + M::NX;
         const size_t nV = (size_t)(N + 1) * SG, nPI = (size_t)N * M::NX, nL = (size_t)N * 2 * SG;
-        buf.assign((size_t)B * (2 * nV + nPI + nL + M::NX + M::NP), T(0));
+        const size_t nY = (size_t)N * SG + M::NX;
+        buf.assign((size_t)B * (nV + nY + nPI + nL + M::NX + M::NP), T(0));
         T* p = buf.data();
-        gs.V = p; p += B * nV; gs.PI = p; p += B * nPI; gs.LAM = p; p += B * nL; gs.YREF = p; p += B * nV; gs.X0 = p; p += (size_t)B * M::NX; gs.PAR = p;
+        gs.V = p; p += B * nV; gs.PI = p; p += B * nPI; gs.LAM = p; p += B * nL; gs.YREF = p; p += B * nY; gs.X0 = p; p += (size_t)B * M::NX; gs.PAR = p;
         ints.assign((size_t)4 * B, 0);
         gs.status = ints.data(); gs.sqp_iter = gs.status + B; gs.qp_iter = gs.sqp_iter + B; gs.have_mult = gs.qp_iter + B;
         gs.B = B; gs.N = N;
+        u0.assign((size_t)B * M::NU, 0.0); gs.U0 = u0.data();
         sm.assign(SmLayout<M, true>::elems(N), T(0));
     }
     void set(int inst, int field, int k, const double* v) {

@@ -309,6 +309,16 @@ def test_acados_surface_fields_and_helpers():
     qp1 = s.get_stats('qp_iter').cpu().numpy().copy()
     s.reset(); s.set_yref_all(yref); s.solve_for_x0(torch.tensor(x0))
     assert np.array_equal(s.get_stats('qp_iter').cpu().numpy(), qp1) and np.array_equal(qp1, want['qp_iter'])
+    # the zero-allocation host form used by bench.py's e2e leg, and the FP32 variant of the same call
+    s.reset(); s.set_yref_all(torch.tensor(yref).pin_memory())
+    uh = torch.empty((B, nu), dtype=torch.float64).pin_memory(); sh = torch.empty(B, dtype=torch.int32).pin_memory()
+    s.solve_for_x0_into(torch.tensor(x0).pin_memory(), uh, sh)
+    np.testing.assert_allclose(uh.numpy(), want['u'][:, 0], rtol=0, atol=1e-9)
+    assert np.array_equal(sh.numpy(), want['status'])
+    s32 = pkg.BatchedAcadosOcpSolver('force', batch=B, device=0, precision='fp32')
+    s32.set_yref_all(yref)
+    u32 = s32.solve_for_x0(x0, fail_on_nonzero_status=False)
+    np.testing.assert_allclose(torch.as_tensor(u32).cpu().numpy(), want['u'][:, 0], rtol=0, atol=5e-4)
     # B = 1: numpy in, numpy out, int status - what the reference's follow_trajectory relies on
     s1 = pkg.BatchedAcadosOcpSolver('force', batch=1, device=0)
     for k in range(N):
