@@ -16,3 +16,15 @@ def store_data(path_prefix, Xsim, a, U_opt_plant):
     np.save(path_prefix + '_xsim.npy', np.asarray(Xsim))
     np.save(path_prefix + '_a.npy', np.asarray(a))
     np.save(path_prefix + '_uopt.npy', np.asarray(U_opt_plant))
+
+
+def export_instance(results, ref, instance=0, dt=1 / 50):
+    """One drone of a batched run in the layout reference src/store_results.py:215-230 (`create_plots(dt, XRef, XSim, a,
+    UOpt)`) and src/main.py:21-22 use: (dt, XRef [S, >=4], XSim [S, 4], a [S, 2], UOpt [S, 2]) as numpy arrays.
+    `results` is BatchedClosedLoop.results(); `ref` the trajectory table of that drone ([rows, 8]) or of all ([B, rows, 8])."""
+    to_np = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    xsim = to_np(results['Xsim'][instance])
+    S = xsim.shape[0] - 1
+    r = to_np(ref)
+    r = r[instance] if r.ndim == 3 else r
+    return dt, r[:S], xsim[:S], to_np(results['a'][instance]), to_np(results['U_plant'][instance])

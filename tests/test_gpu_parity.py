@@ -378,3 +378,26 @@ def test_odd_shapes(model):
         assert np.array_equal(s.get_stats('qp_iter').cpu().numpy(), want['qp_iter']), (B, N)
         np.testing.assert_allclose(s.get(0, 'u').cpu().numpy(), want['u'][:, 0], rtol=0, atol=1e-9, err_msg=str((B, N)))
         np.testing.assert_allclose(s.get(N, 'x').cpu().numpy(), want['x'][:, N], rtol=0, atol=1e-9, err_msg=str((B, N)))
+
+
+@pytest.mark.parametrize('model', ['force', 'jerk'])
+def test_controller_parameters_per_instance(model):
+    """BASELINE config 4, second run: the controller model gets the perturbed plant mass as its parameter p (north-star:
+    set/get of `p`).  Fused loop with p_ctrl = p_plant, and set(0, 'p', ...) on the step-by-step surface."""
+    B, S = 40, 25
+    om = MODEL_ID[model]
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=23, mass_sigma=0.08)
+    want = co.closed_loop(co.default_opts(om), refs, x0, noise, pp, pp, S)          # controller knows the true mass
+    got, _ = _run_loop(model, refs, x0, noise, pp, pp, S)
+    assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
+    for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
+        np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-9, err_msg=k)
+    nominal = co.closed_loop(co.default_opts(om), refs, x0, noise, pc, pp, S)
+    if model == 'force':                                                            # the mass enters the force model's B matrix
+        assert np.abs(nominal['U_ctrl'] - want['U_ctrl']).max() > 1e-4
+    x0s, yref = random_solve_inputs(om, B, seed=29)
+    w1 = co.solve_batch(co.default_opts(om), x0s, yref, pp)
+    s = pkg.BatchedAcadosOcpSolver(model, batch=B, device=0)
+    s.set(0, 'p', pp); s.set_yref_all(yref)
+    np.testing.assert_allclose(s.solve_for_x0(torch.tensor(x0s), fail_on_nonzero_status=False).cpu().numpy(), w1['u'][:, 0], rtol=0, atol=1e-9)
+    np.testing.assert_array_equal(s.get(0, 'p').cpu().numpy(), pp)
