@@ -28,7 +28,7 @@ struct Handle {
     bnmpc_config cfg;
     Opts opts;
     const ModelOps* ops;
-    int batch, device, ctas;       // ctas: persistent CTAs per launch
+    int batch, device, ctas, warps;    // persistent CTAs per launch (one per SM) and warps per CTA (instances in flight per SM)
     int *queue, qi;                // work-queue counters (one per launch, recycled), next counter to use
     cudaStream_t stream;
     bool own_stream;
@@ -306,6 +306,7 @@ int bnmpc_config_default(int model, bnmpc_config* c) {
     return 0;
 }
 
+
 int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) {
     if (!cfg || !handle) return fail(BNMPC_E_ARG, "NULL argument");
     if (batch < 1) return fail(BNMPC_E_ARG, "batch must be >= 1");
@@ -319,8 +320,8 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return fail(BNMPC_E_CUDA, "no CUDA device: libbnmpc has no CPU path");
     if (device < 0 || device >= ndev) return fail(BNMPC_E_ARG, "device index out of range");
-    if (ops->smem_bytes(cfg->horizon) * BNMPC_WARPS_PER_CTA > 226 * 1024 || ops->tmem_cols(cfg->horizon) == 0)
-        return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of a CTA exceeds 227 KB of shared memory or 512 tensor-memory columns");
+    if (ops->smem_bytes(cfg->horizon) > 226 * 1024 || ops->tmem_cols(cfg->horizon, 1) == 0)
+        return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of one instance exceeds 227 KB of shared memory or 512 tensor-memory columns");
     CK(cudaSetDevice(device));
     Handle* h = new Handle();
     memset(h, 0, sizeof(*h));
@@ -362,17 +363,20 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     h->gs.status = h->ints; h->gs.sqp_iter = h->ints + batch; h->gs.qp_iter = h->ints + 2 * batch; h->gs.have_mult = h->ints + 3 * batch;
     h->gs.B = batch; h->gs.N = cfg->horizon;
     {
-        int per_sm = 0;
+        int warps = 0;
         cudaDeviceProp pr;
         CKH(cudaGetDeviceProperties(&pr, device));
-        CKH(ops->max_ctas_per_sm(cfg->horizon, &per_sm));
-        if (per_sm < 1) { bnmpc_destroy(h); return fail(BNMPC_E_UNSUPPORTED, "kernel does not fit on an SM for this horizon"); }
-        if (const char* e = getenv("BNMPC_CTAS_PER_SM")) {      // tuning knob: fewer resident CTAs per SM than would fit
+        CKH(ops->cta_shape(cfg->horizon, &warps));
+        if (warps < 1) { bnmpc_destroy(h); return fail(BNMPC_E_UNSUPPORTED, "kernel does not fit on an SM for this horizon"); }
+        if (const char* e = getenv("BNMPC_WARPS_PER_SM")) {     // tuning knob: fewer instances in flight per SM than would fit
             const int v = atoi(e);
-            if (v >= 1 && v < per_sm) per_sm = v;
+            if (v >= 1 && v < warps) warps = v;
         }
-        const int want = (batch + BNMPC_WARPS_PER_CTA - 1) / BNMPC_WARPS_PER_CTA;
-        h->ctas = want < per_sm * pr.multiProcessorCount ? want : per_sm * pr.multiProcessorCount;
+        if (batch < warps * pr.multiProcessorCount)             // small batches spread over the SMs instead of filling a few
+            warps = (batch + pr.multiProcessorCount - 1) / pr.multiProcessorCount;
+        h->warps = warps;
+        const int want = (batch + warps - 1) / warps;
+        h->ctas = want < pr.multiProcessorCount ? want : pr.multiProcessorCount;
     }
     CKH(cudaMemsetAsync(h->queue, 0, sizeof(int) * QUEUE_LEN, h->stream));
     h->qi = 0;
@@ -499,7 +503,7 @@ int bnmpc_solve(void* handle) {
     if (use_device(h)) return BNMPC_E_CUDA;
     int* q;
     if (int rc = next_queue(h, &q)) return rc;
-    CK(h->ops->solve(h->gs, h->opts, h->ctas, q, h->stream)); h->launches++;
+    CK(h->ops->solve(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
     return 0;
 }
 
@@ -519,7 +523,7 @@ int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* stat
     }
     int* q;
     if (int rc = next_queue(h, &q)) return rc;
-    CK(h->ops->solve(h->gs, h->opts, h->ctas, q, h->stream)); h->launches++;
+    CK(h->ops->solve(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
     if (u0) CK(cudaMemcpyAsync(u0, h->gs.U0, sizeof(double) * B * nu, out, h->stream));   // gathered by the solve kernel
     if (status) CK(cudaMemcpyAsync(status, h->gs.status, sizeof(int32_t) * B, out, h->stream));
     if (!on_device) CK(cudaStreamSynchronize(h->stream));
@@ -605,7 +609,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
         la.step = a->first_step + s;
         int* q;
         if (int rc = next_queue(h, &q)) return rc;
-        CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, q, h->stream)); h->launches++;
+        CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream)); h->launches++;
     }
     return 0;
 }

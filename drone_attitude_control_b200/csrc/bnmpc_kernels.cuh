@@ -2,29 +2,35 @@
 // Each model_*.cu instantiates BNMPC_DEFINE_MODEL_OPS for one generated model (both precisions); bnmpc_api.cu only
 // sees the ModelOps table, so the heavy templates compile in parallel translation units.
 //
-// Launch shape: PERSISTENT CTAs of 4 warps; every warp pulls OCP instances from an atomic work queue and solves them
-// one at a time (instance solve lengths differ by 4x, so the queue balances itself).  Warps of a CTA never synchronise
-// during the solves; the CTA exists because of tensor memory:
+// Launch shape: ONE PERSISTENT CTA per SM with as many warps as the on-chip memories hold instances (14 for the force
+// model at N = 30); every warp pulls OCP instances from an atomic work queue and solves them one at a time (instance
+// solve lengths differ by 4x, so the queue balances itself).  Warps of a CTA never synchronise during the solves; the
+// CTA exists because of tensor memory:
 //
 //   * shared memory holds the part of an instance's working set that the Riccati sweeps and neighbouring stages touch
 //     (SmLayout<M,false>: 31 doubles per (stage, block) item for the force model, 15.4 KB per instance);
 //   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t: 15 doubles per item).  A warp
-//     owns the 32 TMEM lanes of its quarter; lane l keeps the records of its items in consecutive columns and moves a
-//     whole record with one tcgen05.ld / tcgen05.st (.32x32b.x32).  TMEM is used purely as a software-managed,
+//     owns the 32 TMEM lanes of its quarter (warp id mod 4) in the column group of its warp quad (warp id / 4); lane l
+//     keeps the records of its items in consecutive columns and moves a whole record with one tcgen05.ld / tcgen05.st
+//     (.32x32b.x32).  TMEM is used purely as a software-managed,
 //     lane-private scratchpad - no tcgen05.mma is involved: these are 3x3 / 4x4 FP64 problems.
 //
-// This raises the instances in flight per SM from 8 to 12-16.  BNMPC_CTAS_PER_SM = 3 (12 warps, 168 registers per
-// thread) measured faster than 4 (16 warps, 128 registers, spills): 5.0 M vs 4.6 M solves/s at 65536 instances.
+// This raises the instances in flight per SM from 8 to 12.  Measured (force model, 65536 instances, M solves/s): ONE CTA of
+// 12 warps at 168 registers 7.20; three CTAs of 4 warps at 168 registers 6.20; one CTA at 128 registers with 8 / 10 / 11 /
+// 12 / 13 / 14 warps 5.03 / 5.08 / 5.58 / 6.57 / 5.87 / 6.04 - only whole multiples of the four SM sub-partitions pay, and
+// registers beat a 4th warp per sub-partition.  The launch bound is therefore per model: the largest multiple of four
+// warps (at most BNMPC_MAX_WARPS = 12) whose instances fit shared memory at the reference horizon N = 30 - 12 for the
+// force model (168 registers), 8 for the jerk model (255 registers).  The warps actually launched per CTA follow from the
+// horizon of the handle and the tensor-memory columns (cta_shape below).
 #pragma once
 #include <cuda_runtime.h>
 #include <string.h>
 
 #include "bnmpc_loop.cuh"
 
-#ifndef BNMPC_CTAS_PER_SM
-#define BNMPC_CTAS_PER_SM 3      // resident CTAs per SM the register allocator leaves room for (launch bound)
+#ifndef BNMPC_MAX_WARPS
+#define BNMPC_MAX_WARPS 12       // warps of the one resident CTA per SM the register allocator leaves room for (launch bound)
 #endif
-#define BNMPC_WARPS_PER_CTA 4
 
 namespace bnmpc {
 
@@ -44,10 +50,10 @@ struct ModelOps {
     const char* name;
     int nx, nu, np, nblk, nxb, nub, kind, jac_const, elem_size, sm_rows;
     size_t (*smem_bytes)(int N);                                    // dynamic shared memory of one instance (one warp)
-    int (*tmem_cols)(int N);                                        // tensor-memory columns one CTA allocates (0 = too many)
-    cudaError_t (*solve)(const GsAny&, const Opts&, int ctas, int* queue, cudaStream_t);
-    cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int* queue, cudaStream_t);
-    cudaError_t (*max_ctas_per_sm)(int N, int* out);
+    int (*tmem_cols)(int N, int warps);                             // tensor-memory columns a CTA of `warps` allocates (0 = too many)
+    cudaError_t (*solve)(const GsAny&, const Opts&, int ctas, int warps, int* queue, cudaStream_t);
+    cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
+    cudaError_t (*cta_shape)(int N, int* warps);                    // warps per CTA (= instances in flight per SM), 0 = does not fit
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -92,12 +98,19 @@ struct TmemPriv {
     static constexpr int CPR = CH * 32;                            // columns per round of items
     uint32_t base;                                                 // lane quarter of this warp | first column
 
-    static __host__ __device__ int cols_needed(int N) {            // power of two >= 32, 0 if it does not fit
-        const int rounds = ((N + 1) * M::NBLK + 31) / 32;
-        const int need = rounds * CPR;
+    static __host__ __device__ int cols_per_quad(int N) {          // columns the four warps of a quad share (one lane quarter each)
+        return ((N + 1) * M::NBLK + 31) / 32 * CPR;
+    }
+    static __host__ __device__ int cols_needed(int N, int warps) { // allocation of a CTA: power of two >= 32, 0 if it does not fit
+        const int need = (warps + 3) / 4 * cols_per_quad(N);
         int c = 32;
         while (c < need) c <<= 1;
         return c <= 512 ? c : 0;
+    }
+    // TMEM address of this warp's records: lane quarter = warp id mod 4 (the hardware's access rule), column group = warp id / 4
+    static __device__ __forceinline__ uint32_t warp_base(uint32_t tbase, int N) {
+        const uint32_t w = threadIdx.x >> 5;
+        return tbase + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)cols_per_quad(N);
     }
     __device__ __forceinline__ void load(T*, int rd, int, bool, PrivRec<T, s>& r) const {
         __syncwarp();                                              // tcgen05.ld/st are warp-collective (.aligned)
@@ -163,6 +176,14 @@ __device__ __forceinline__ int warp_smem_off(int stride_elems) {
     return off;
 }
 
+// launch bound of a model: instances that fit shared memory at the reference horizon, whole warp quads, <= BNMPC_MAX_WARPS
+template <class M, class T>
+struct LaunchShape {
+    static constexpr size_t REF_BYTES = ((size_t)SmLayout<M, false>::STRIDE * (31 * M::NBLK) + M::NX) * sizeof(T);
+    static constexpr int FIT = (int)((227 * 1024 - 1024) / REF_BYTES);
+    static constexpr int MAX_WARPS = FIT >= BNMPC_MAX_WARPS ? BNMPC_MAX_WARPS : (FIT >= 4 ? FIT / 4 * 4 : (FIT >= 1 ? FIT : 1));
+};
+
 // next instance of the work queue (one atomic per warp)
 __device__ __forceinline__ int next_instance(int* queue) {
     int i = 0;
@@ -171,22 +192,22 @@ __device__ __forceinline__ int next_instance(int* queue) {
 }
 
 template <class M, class T>
-__global__ void __launch_bounds__(32 * BNMPC_WARPS_PER_CTA, BNMPC_CTAS_PER_SM)
+__global__ void __launch_bounds__(32 * LaunchShape<M, T>::MAX_WARPS, 1)
 k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, int* queue, int tmem_cols) {
     const uint32_t tbase = tmem_alloc_cta(tmem_cols);
     const WarpGroup<32> g;
-    const TmemPriv<M, T> ps{tbase + (((threadIdx.x >> 5) * 32u) << 16)};
+    const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
     Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
     for (int inst = next_instance(queue); inst < gs.B; inst = next_instance(queue)) api_solve<M, T>(sv, inst, gs);
     tmem_free_cta(tbase, tmem_cols);
 }
 
 template <class M, class T>
-__global__ void __launch_bounds__(32 * BNMPC_WARPS_PER_CTA, BNMPC_CTAS_PER_SM)
+__global__ void __launch_bounds__(32 * LaunchShape<M, T>::MAX_WARPS, 1)
 k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a, int* queue, int tmem_cols) {
     const uint32_t tbase = tmem_alloc_cta(tmem_cols);
     const WarpGroup<32> g;
-    const TmemPriv<M, T> ps{tbase + (((threadIdx.x >> 5) * 32u) << 16)};
+    const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
     Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
     for (int inst = next_instance(queue); inst < gs.B; inst = next_instance(queue)) closed_loop_step<M, T>(sv, inst, gs, a);
     tmem_free_cta(tbase, tmem_cols);
@@ -195,7 +216,7 @@ k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, co
 template <class M, class T>
 struct OpsImpl {
     static size_t smem_bytes(int N) { return (SmLayout<M, false>::elems(N) * sizeof(T) + 15) / 16 * 16; }
-    static int tmem_cols(int N) { return TmemPriv<M, T>::cols_needed(N); }
+    static int tmem_cols(int N, int warps) { return TmemPriv<M, T>::cols_needed(N, warps); }
     // dynamic shared memory is opted in once per kernel up to the device limit (handles with different horizons share
     // the kernel, so the attribute must not follow the last handle created)
     template <class K>
@@ -209,42 +230,40 @@ struct OpsImpl {
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
-    static cudaError_t max_ctas_per_sm(int N, int* out) {
-        const size_t bytes = smem_bytes(N) * BNMPC_WARPS_PER_CTA;
-        cudaError_t e = prep(k_loop_step<M, T>, bytes);
+    // Warps of the one CTA per SM = instances in flight per SM: bounded by registers (the launch bound), by shared memory
+    // (the opt-in maximum of a block minus the static part) and by tensor memory (512 columns, one column group per warp quad).
+    static cudaError_t cta_shape(int N, int* warps) {
+        cudaError_t e = prep(k_loop_step<M, T>, 0);
         if (e != cudaSuccess) return e;
-        e = prep(k_solve<M, T>, bytes);
+        e = prep(k_solve<M, T>, 0);
         if (e != cudaSuccess) return e;
-        // resident CTAs per SM: registers (the launch bound), shared memory (228 KB per SM, 1 KB reserved per CTA) and
-        // tensor memory (512 columns per SM; every resident CTA must get its columns or tcgen05.alloc would block)
-        int dev = 0, smem_sm = 0;
+        int dev = 0, optin = 0;
         e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
-        int r = BNMPC_CTAS_PER_SM;
-        const int by_smem = (int)((size_t)smem_sm / (bytes + 1024));
-        if (by_smem < r) r = by_smem;
-        const int cols = tmem_cols(N);
-        if (cols > 0 && 512 / cols < r) r = 512 / cols;
-        *out = r;
+        int w = (int)((size_t)(optin - 1024) / smem_bytes(N));
+        if (w > LaunchShape<M, T>::MAX_WARPS) w = LaunchShape<M, T>::MAX_WARPS;
+        while (w > 0 && tmem_cols(N, w) == 0) w--;
+        if (w > 4) w = w / 4 * 4;                                // whole warp quads: one warp more on one sub-partition costs more than it adds
+        *warps = w;
         return cudaSuccess;
     }
-    static cudaError_t solve(const GsAny& a, const Opts& o_, int ctas, int* queue, cudaStream_t st) {
+    static cudaError_t solve(const GsAny& a, const Opts& o_, int ctas, int warps, int* queue, cudaStream_t st) {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
-        k_solve<M, T><<<ctas, 32 * BNMPC_WARPS_PER_CTA, smem_bytes(o.N) * BNMPC_WARPS_PER_CTA, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N));
+        k_solve<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps));
         return cudaGetLastError();
     }
-    static cudaError_t loop_step(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int* queue, cudaStream_t st) {
+    static cudaError_t loop_step(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int* queue, cudaStream_t st) {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
-        k_loop_step<M, T><<<ctas, 32 * BNMPC_WARPS_PER_CTA, smem_bytes(o.N) * BNMPC_WARPS_PER_CTA, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N));
+        k_loop_step<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N, warps));
         return cudaGetLastError();
     }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        SmLayout<M, false>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &max_ctas_per_sm};
+                        SmLayout<M, false>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &cta_shape};
     }
 };
 
