@@ -29,7 +29,7 @@
 #include "bnmpc_loop.cuh"
 
 #ifndef BNMPC_MAX_WARPS
-#define BNMPC_MAX_WARPS 12       // warps of the one resident CTA per SM the register allocator leaves room for (launch bound)
+#define BNMPC_MAX_WARPS 16       // warps of the one resident CTA per SM the register allocator leaves room for (launch bound)
 #endif
 
 namespace bnmpc {
