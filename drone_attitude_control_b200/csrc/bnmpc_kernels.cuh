@@ -91,10 +91,11 @@ __device__ __forceinline__ float words_to(uint32_t lo, uint32_t, float) { return
 template <class M, class T>
 struct TmemPriv {
     static constexpr bool IN_SMEM = false;
-    static constexpr int s = M::NXB + M::NUB;
+    static constexpr int s = M::NXB + M::NUB, n = M::NXB;
     static constexpr int WPE = (int)sizeof(T) / 4;                 // 32-bit words per element
-    static constexpr int NE = 5 * s;                               // elements of a record: q, lam, t
-    static constexpr int CH = (NE * WPE + 31) / 32;                // .x32 chunks per record
+    static constexpr int CH = (5 * s * WPE + 31) / 32;             // .x32 chunks per record (q, lam, t)
+    static constexpr bool QB_PRIV = (5 * s + n) * WPE <= CH * 32;  // room for the dynamics offset b_k in the same chunks
+    static constexpr int NE = 5 * s + (QB_PRIV ? n : 0);           // elements of a record: q, lam, t [, b]
     static constexpr int CPR = CH * 32;                            // columns per round of items
     uint32_t base;                                                 // lane quarter of this warp | first column
 
@@ -112,7 +113,7 @@ struct TmemPriv {
         const uint32_t w = threadIdx.x >> 5;
         return tbase + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)cols_per_quad(N);
     }
-    __device__ __forceinline__ void load(T*, int rd, int, bool, PrivRec<T, s>& r) const {
+    __device__ __forceinline__ void load(T*, int rd, int, bool, PrivRec<T, s, n>& r) const {
         __syncwarp();                                              // tcgen05.ld/st are warp-collective (.aligned)
         uint32_t w[CH * 32];
 #pragma unroll
@@ -125,13 +126,21 @@ struct TmemPriv {
         for (int v = 0; v < s; v++) r.q[v] = e[v];
 #pragma unroll
         for (int v = 0; v < 2 * s; v++) { r.lam[v] = e[s + v]; r.tt[v] = e[3 * s + v]; }
+        if constexpr (QB_PRIV) {
+#pragma unroll
+            for (int v = 0; v < n; v++) r.qb[v] = e[5 * s + v];
+        }
     }
-    __device__ __forceinline__ void store(T*, int rd, int, bool, const PrivRec<T, s>& r) const {
+    __device__ __forceinline__ void store(T*, int rd, int, bool, const PrivRec<T, s, n>& r) const {
         T e[NE];
 #pragma unroll
         for (int v = 0; v < s; v++) e[v] = r.q[v];
 #pragma unroll
         for (int v = 0; v < 2 * s; v++) { e[s + v] = r.lam[v]; e[3 * s + v] = r.tt[v]; }
+        if constexpr (QB_PRIV) {
+#pragma unroll
+            for (int v = 0; v < n; v++) e[5 * s + v] = r.qb[v];
+        }
         uint32_t w[CH * 32];
         __syncwarp();
 #pragma unroll
@@ -179,7 +188,7 @@ __device__ __forceinline__ int warp_smem_off(int stride_elems) {
 // launch bound of a model: instances that fit shared memory at the reference horizon, whole warp quads, <= BNMPC_MAX_WARPS
 template <class M, class T>
 struct LaunchShape {
-    static constexpr size_t REF_BYTES = ((size_t)SmLayout<M, false>::STRIDE * (31 * M::NBLK) + M::NX) * sizeof(T);
+    static constexpr size_t REF_BYTES = ((size_t)SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::STRIDE * (31 * M::NBLK) + M::NX) * sizeof(T);
     static constexpr int FIT = (int)((227 * 1024 - 1024) / REF_BYTES);
     static constexpr int MAX_WARPS = FIT >= BNMPC_MAX_WARPS ? BNMPC_MAX_WARPS : (FIT >= 4 ? FIT / 4 * 4 : (FIT >= 1 ? FIT : 1));
 };
@@ -215,7 +224,7 @@ k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, co
 
 template <class M, class T>
 struct OpsImpl {
-    static size_t smem_bytes(int N) { return (SmLayout<M, false>::elems(N) * sizeof(T) + 15) / 16 * 16; }
+    static size_t smem_bytes(int N) { return (SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::elems(N) * sizeof(T) + 15) / 16 * 16; }
     static int tmem_cols(int N, int warps) { return TmemPriv<M, T>::cols_needed(N, warps); }
     // dynamic shared memory is opted in once per kernel up to the device limit (handles with different horizons share
     // the kernel, so the attribute must not follow the last handle created)
@@ -263,7 +272,7 @@ struct OpsImpl {
     }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        SmLayout<M, false>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &cta_shape};
+                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &cta_shape};
     }
 };
 
