@@ -30,6 +30,7 @@ struct Handle {
     const ModelOps* ops;
     int batch, device, ctas, warps;    // persistent CTAs per launch (one per SM) and warps per CTA (instances in flight per SM)
     int *queue, qi;                // work-queue counters (one per launch, recycled), next counter to use
+    int* order;                    // queue position -> instance, refreshed before every launch (longest expected solve first)
     cudaStream_t stream;
     bool own_stream;
     GsAny gs;                      // persistent per-instance state in HBM
@@ -254,6 +255,37 @@ int next_queue(Handle* h, int** q) {
     return 0;
 }
 
+// Longest-expected-first order of the work queue: counting sort of the instances by the interior-point iterations (plus
+// the SQP iterations, which carry the linearisation) of their previous solve, descending.  One CTA; the order among equal
+// keys is arbitrary, which is fine - the order only moves work in time.
+__global__ void k_order(const int32_t* __restrict__ qp_iter, const int32_t* __restrict__ sqp_iter, int B, int* __restrict__ order) {
+    __shared__ int hist[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        int k = qp_iter[i] + 2 * sqp_iter[i];
+        atomicAdd(&hist[k > 255 ? 255 : (k < 0 ? 0 : k)], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {            // start of bucket k = number of instances with a larger key
+        int run = 0;
+        for (int k = 255; k >= 0; k--) { const int c = hist[k]; hist[k] = run; run += c; }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        int k = qp_iter[i] + 2 * sqp_iter[i];
+        order[atomicAdd(&hist[k > 255 ? 255 : (k < 0 ? 0 : k)], 1)] = i;
+    }
+}
+
+// refresh the queue order before a launch (only when there are more instances than warps in flight)
+int refresh_order(Handle* h) {
+    if (!h->opts.order) return 0;
+    k_order<<<1, 1024, 0, h->stream>>>(h->gs.qp_iter, h->gs.sqp_iter, h->batch, h->order);
+    CK(cudaGetLastError()); h->launches++;
+    return 0;
+}
+
 int reset_iterate(Handle* h) {
     const size_t es = h->ops->elem_size, B = h->batch;
     CK(cudaMemsetAsync(h->gs.V, 0, B * h->nV * es, h->stream));
@@ -349,6 +381,7 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     ok = ok && cudaMalloc(&h->queue, sizeof(int) * QUEUE_LEN) == cudaSuccess;
     ok = ok && cudaMalloc(&h->xs, sizeof(double) * 11 * h->Bp) == cudaSuccess;
     ok = ok && cudaMalloc(&h->gs.U0, sizeof(double) * (size_t)batch * ops->nu) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->order, sizeof(int) * (size_t)batch) == cudaSuccess;
     if (!ok) {
         const std::string msg = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
         bnmpc_destroy(h);
@@ -377,6 +410,9 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
         h->warps = warps;
         const int want = (batch + warps - 1) / warps;
         h->ctas = want < pr.multiProcessorCount ? want : pr.multiProcessorCount;
+        // longest-first order: pays from about two instances per warp on (measured: +3 % at 3.5 per warp, +5 % for the jerk
+        // model at 2.3, -2 % at 1.7 where the extra launch costs more than the shorter tail saves)
+        h->opts.order = (batch > 2 * h->ctas * warps && !getenv("BNMPC_NO_ORDER")) ? h->order : nullptr;
     }
     CKH(cudaMemsetAsync(h->queue, 0, sizeof(int) * QUEUE_LEN, h->stream));
     h->qi = 0;
@@ -402,6 +438,7 @@ int bnmpc_destroy(void* handle) {
     if (h->gs_base) cudaFree(h->gs_base);
     if (h->ints) cudaFree(h->ints);
     if (h->queue) cudaFree(h->queue);
+    if (h->order) cudaFree(h->order);
     if (h->xs) cudaFree(h->xs);
     if (h->gs.U0) cudaFree(h->gs.U0);
     for (int i = 0; i < 4; i++) if (h->stage[i]) cudaFree(h->stage[i]);
@@ -501,6 +538,7 @@ int bnmpc_solve(void* handle) {
     Handle* h = (Handle*)handle;
     if (!h) return fail(BNMPC_E_ARG, "NULL handle");
     if (use_device(h)) return BNMPC_E_CUDA;
+    if (int rc = refresh_order(h)) return rc;
     int* q;
     if (int rc = next_queue(h, &q)) return rc;
     CK(h->ops->solve(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
@@ -521,6 +559,7 @@ int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* stat
         if (int rc = stage_in(h, 0, x0, (size_t)B * nx, on_device, &d)) return rc;
         CK(field_xfer(h, F_LBX, 0, const_cast<double*>(d), nx, nx, 1));
     }
+    if (int rc = refresh_order(h)) return rc;
     int* q;
     if (int rc = next_queue(h, &q)) return rc;
     CK(h->ops->solve(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
@@ -607,6 +646,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     la.xs = h->xs; la.acc = h->acc; la.cost = h->cost; la.abs_err = h->abs_err; la.p_plant = h->p_plant;
     for (int s = 0; s < a->n_steps; s++) {
         la.step = a->first_step + s;
+        if (int rc = refresh_order(h)) return rc;
         int* q;
         if (int rc = next_queue(h, &q)) return rc;
         CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream)); h->launches++;

@@ -193,10 +193,15 @@ struct LaunchShape {
     static constexpr int MAX_WARPS = FIT >= BNMPC_MAX_WARPS ? BNMPC_MAX_WARPS : (FIT >= 4 ? FIT / 4 * 4 : (FIT >= 1 ? FIT : 1));
 };
 
-// next instance of the work queue (one atomic per warp)
-__device__ __forceinline__ int next_instance(int* queue) {
+// next instance of the work queue (one atomic per warp).  `order` maps the queue position to an instance: the host side
+// sorts the instances by the iterations of their previous solve, longest first, so that the tail of a launch is made of
+// short solves (instances are independent: the order changes the timing, never a result).
+__device__ __forceinline__ int next_instance(int* queue, const int* order, int B) {
     int i = 0;
-    if ((threadIdx.x & 31) == 0) i = atomicAdd(queue, 1);
+    if ((threadIdx.x & 31) == 0) {
+        i = atomicAdd(queue, 1);
+        if (order != nullptr && i < B) i = order[i];
+    }
     return __shfl_sync(0xffffffffu, i, 0);
 }
 
@@ -207,7 +212,7 @@ k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, int* q
     const WarpGroup<32> g;
     const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
     Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
-    for (int inst = next_instance(queue); inst < gs.B; inst = next_instance(queue)) api_solve<M, T>(sv, inst, gs);
+    for (int inst = next_instance(queue, o.order, gs.B); inst < gs.B; inst = next_instance(queue, o.order, gs.B)) api_solve<M, T>(sv, inst, gs);
     tmem_free_cta(tbase, tmem_cols);
 }
 
@@ -218,7 +223,7 @@ k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, co
     const WarpGroup<32> g;
     const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
     Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
-    for (int inst = next_instance(queue); inst < gs.B; inst = next_instance(queue)) closed_loop_step<M, T>(sv, inst, gs, a);
+    for (int inst = next_instance(queue, o.order, gs.B); inst < gs.B; inst = next_instance(queue, o.order, gs.B)) closed_loop_step<M, T>(sv, inst, gs, a);
     tmem_free_cta(tbase, tmem_cols);
 }
 
