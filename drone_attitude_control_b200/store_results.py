@@ -28,3 +28,27 @@ def export_instance(results, ref, instance=0, dt=1 / 50):
     r = to_np(ref)
     r = r[instance] if r.ndim == 3 else r
     return dt, r[:S], xsim[:S], to_np(results['a'][instance]), to_np(results['U_plant'][instance])
+
+
+def store_instance(path_prefix, results, ref, instance=0):
+    """`store_data` of the reference (src/store_results.py:11-18: XRef, XSim, UOpt as .npy) for one drone of a batched
+    run; returns the three paths like the reference does."""
+    _, xref, xsim, _, uopt = export_instance(results, ref, instance)
+    paths = tuple(f'{path_prefix}_{name}.npy' for name in ('XRef', 'XSim', 'UOpt'))
+    for path, arr in zip(paths, (xref, xsim, uopt)):
+        np.save(path, arr)
+    return paths
+
+
+def batch_statistics(results, percentiles=(5, 50, 95)):
+    """Monte-Carlo summary of a batched run: mean and percentiles of the per-drone closed-loop cost
+    (controller.py:40-41,54) and of calc_aed per drone (store_results.py:233-236), solver status histogram (acados
+    codes 0-4 over all drones and steps) and the mean / max interior-point iterations per control step."""
+    to_np = lambda t: t.detach().cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t)
+    cost, aed, status, qp = (to_np(results[k]) for k in ('cost', 'aed', 'status', 'qp_iter'))
+    out = {'n': int(cost.shape[0])}
+    for name, v in (('cost', cost), ('aed', aed)):
+        out[name] = {'mean': float(v.mean()), **{f'p{q}': float(np.percentile(v, q)) for q in percentiles}, 'max': float(v.max())}
+    out['status_hist'] = {int(c): int((status == c).sum()) for c in range(5)}
+    out['qp_iter'] = {'mean': float(qp.mean()), 'max': int(qp.max())}
+    return out

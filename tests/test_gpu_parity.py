@@ -401,3 +401,55 @@ def test_controller_parameters_per_instance(model):
     s.set(0, 'p', pp); s.set_yref_all(yref)
     np.testing.assert_allclose(s.solve_for_x0(torch.tensor(x0s), fail_on_nonzero_status=False).cpu().numpy(), w1['u'][:, 0], rtol=0, atol=1e-9)
     np.testing.assert_array_equal(s.get(0, 'p').cpu().numpy(), pp)
+
+
+@pytest.mark.parametrize('family', ['static', 'straight', 'square'])
+@pytest.mark.parametrize('model', ['force', 'jerk'])
+def test_other_trajectory_families(model, family):
+    """the reference's other trajectory families (src/jerk_model/gen_trajectory.py), batched.  The square has
+    velocity discontinuities at its corners and drives the bounds active; parity against the oracle as for the circle."""
+    from drone_attitude_control_b200 import generate_trajectory as gt
+    B, S = 24, 140
+    om = MODEL_ID[model]
+    rng = np.random.default_rng(41)
+    initial = rng.uniform(-0.2, 0.2, (B, 2))
+    length = rng.uniform(0.2, 0.6, B)
+    if family == 'static':
+        ref = gt.gen_static_point_traj_batched(500, 30, initial)
+    elif family == 'straight':
+        ref = gt.gen_straight_traj_batched(500, 30, initial, length)
+    else:
+        ref = gt.gen_square_traj_batched(500, 30, initial, length)
+    refs = ref.numpy()
+    x0 = np.concatenate([initial + rng.uniform(-0.03, 0.03, (B, 2)), rng.uniform(-0.03, 0.03, (B, 2))], axis=1)
+    noise = rng.normal(0, 0.01, (S, B))
+    pc = np.repeat(P_NOM[None], B, 0)
+    want = co.closed_loop(co.default_opts(om), refs, x0, noise, pc, pc, S)
+    got, _ = _run_loop(model, refs, x0, noise, pc, pc, S)
+    assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
+    for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
+        np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-8, err_msg=k)
+    if family == 'static':      # hovering on the point: the position error stays at the noise level
+        assert np.abs(got['Xsim'][:, -1, :2] - initial).max() < 0.1
+    if family == 'square':      # the corners saturate an input: some IPM solves need many more iterations than on a circle
+        assert got['qp_iter'].max() > 12
+
+
+def test_results_surface_for_plotting_and_statistics(tmp_path):
+    """one drone of a batched run in the (dt, XRef, XSim, a, UOpt) layout of create_plots
+    (src/store_results.py:215-230, src/main.py:21-22), store_data-style .npy dumps (:11-18), Monte-Carlo statistics."""
+    from drone_attitude_control_b200 import store_results as sr
+    B, S = 32, 60
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=47)
+    got, _ = _run_loop('force', refs, x0, noise, pc, pp, S)
+    res = {k: torch.tensor(v) for k, v in got.items()}
+    dt, xref, xsim, a, uopt = sr.export_instance(res, refs, instance=5)
+    assert dt == 0.02 and xref.shape == (S, 8) and xsim.shape == (S, 4) and a.shape == (S, 2) and uopt.shape == (S, 2)
+    np.testing.assert_array_equal(xsim, got['Xsim'][5, :S])
+    np.testing.assert_array_equal(xref, refs[5, :S])
+    assert abs(sr.calc_aed(xref[:, :2], xsim[:, :2]) - got['aed'][5]) < 1e-12
+    paths = sr.store_instance(str(tmp_path / 'run'), res, refs, instance=5)
+    np.testing.assert_array_equal(np.load(paths[1]), xsim)
+    st = sr.batch_statistics(res)
+    assert st['n'] == B and st['status_hist'][0] == B * S and st['cost']['p5'] <= st['cost']['p50'] <= st['cost']['p95'] <= st['cost']['max']
+    assert abs(st['aed']['mean'] - got['aed'].mean()) < 1e-15 and st['qp_iter']['max'] == got['qp_iter'].max()

@@ -74,3 +74,32 @@ def test_two_rank_gloo_run_matches_single_rank(tmp_path):
         np.testing.assert_allclose(t['tot'], one['tot'], rtol=1e-13)
         assert t['tot'][2] == B
         assert t['mx'][0] == one['mx'][0]
+
+
+def test_trajectory_families_shapes_and_formulas():
+    """Batched generators of the reference's other trajectory families (src/jerk_model/gen_trajectory.py:8-71) against a
+    direct evaluation of the reference's formulas at the MPC rate."""
+    import numpy as np
+    import torch
+    from drone_attitude_control_b200 import generate_trajectory as gt
+    T, dt, N, NH, g = 10.0, 0.02, 500, 30, 9.81
+    initial = np.array([[0.1, -0.2], [0.0, 0.3]]); length = np.array([0.5, 1.0])
+    st = gt.gen_static_point_traj_batched(N, NH, initial).numpy()
+    assert st.shape == (2, N + NH, 8) and np.all(st[:, :, 0] == initial[:, None, 0]) and np.all(st[:, :, 5] == g) and np.all(st[:, :, 2:5] == 0)
+    sl = gt.gen_straight_traj_batched(N, NH, initial, length).numpy()
+    i = np.arange(N + NH)
+    for b in range(2):
+        jerk = 6 * length[b] / T ** 3
+        np.testing.assert_allclose(sl[b, :, 0], initial[b, 0] + jerk * (i * dt) ** 3 / 6, rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(sl[b, :, 3], 0.5 * jerk * (i * dt) ** 2, rtol=1e-14, atol=1e-15)
+        np.testing.assert_allclose(sl[b, :, 5], jerk * i * dt + g, rtol=1e-14)
+    raw = gt.gen_straight_traj_batched(N, NH, initial, length, fill_acc=False).numpy()
+    assert np.all(raw[:, :, 4] == 0) and np.all(raw[:, :, 5] == g) and np.all(raw[:, :, 6:] == 0)
+    sq = gt.gen_square_traj_batched(N, NH, initial, length).numpy()
+    side = N // 4
+    for b in range(2):
+        L = length[b]
+        np.testing.assert_allclose(sq[b, side - 1, :2], initial[b] + [L * (side - 1) / side, 0], atol=1e-15)
+        np.testing.assert_allclose(sq[b, 2 * side, :2], initial[b] + [L, L], atol=1e-15)
+        np.testing.assert_allclose(sq[b, 3 * side + 1, :2], initial[b] + [0, L - L / side], atol=1e-15)
+        np.testing.assert_allclose(sq[b, N:], sq[b, :NH], atol=0)
