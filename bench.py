@@ -195,13 +195,15 @@ def run_ours(args):
 
         def e2e_step(i, pipelined, last):
             if pipelined:
-                if not last:
-                    prefetch(i + 1)
                 torch.cuda.current_stream().wait_event(yev[i % 2])
                 s.set_yref_all(ydev[i % 2])
+                s.solve_for_x0_into(x0h[i], u_host, st_host, wait=False)   # enqueue: x0 in, solve, u0 + status out (pinned host)
+                if not last:
+                    prefetch(i + 1)      # behind this step's x0 on the H2D engine, concurrent with the solve
+                s.synchronize()          # u0 and status of this step are in host memory
             else:
                 s.set_yref_all(yh[i])
-            s.solve_for_x0_into(x0h[i], u_host, st_host)        # x0 in, u0 + status out (pinned host), returns when they are there
+                s.solve_for_x0_into(x0h[i], u_host, st_host)    # returns when u0 + status are in host memory
 
         def e2e_run(pipelined):
             s.reset()
@@ -224,8 +226,9 @@ def run_ours(args):
         e2e = {'value': e2e_pipe, 'unit': UNIT, 'steps': Ke, 'serial_value': e2e_serial,
                'h2d_bytes_per_step': int(B * (N * ny + nx + 2 * nx) * 8), 'd2h_bytes_per_step': int(B * (nu * 8 + 4)),
                'api': 'BatchedAcadosOcpSolver.set_yref_all (OCP.set_up_ocp) + solve_for_x0 (x0 in, u0 and status out) with pinned host buffers, every step; '
-                      'value: the upload of the next step\'s reference window (known in advance) overlaps the current solve on a copy '
-                      'stream; serial_value: everything on one stream'}
+                      'value: x0 upload, solve and u0/status download are enqueued asynchronously, then the upload of the next step\'s '
+                      'reference window (known in advance) is enqueued on a copy stream and overlaps the solve, then the step waits; '
+                      'serial_value: everything on one stream'}
 
     if rank != 0:
         if world > 1:

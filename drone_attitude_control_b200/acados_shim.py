@@ -191,11 +191,18 @@ class BatchedAcadosOcpSolver:
             return u0[0] if self.batch == 1 else u0
         return u0 if on_dev else torch.from_numpy(u0).to(self.device)
 
-    def solve_for_x0_into(self, x0_host, u0_host, status_host):
+    def solve_for_x0_into(self, x0_host, u0_host, status_host, wait=True):
         """Zero-allocation form for tight loops: pinned host tensors in and out (x0 [B, nx], u0 [B, nu] float64,
-        status [B] int32); returns when the results are in host memory."""
+        status [B] int32); returns when the results are in host memory.  wait=False (BNMPC_HOST_ASYNC) only enqueues the
+        copies and the solve; call synchronize() before reading the outputs - work enqueued in between (e.g. the upload
+        of the next step's reference window on another stream) then runs behind this step's x0 upload, not in front."""
         check(lib().bnmpc_solve_for_x0(self._h, C.c_void_p(x0_host.data_ptr()), C.c_void_p(u0_host.data_ptr()),
-                                       C.c_void_p(status_host.data_ptr()), 0))
+                                       C.c_void_p(status_host.data_ptr()), 0 if wait else 2))
+
+    def solve_for_x0_device(self, x0_dev, u0_dev, status_dev):
+        """Same with device tensors: everything stays on the solver's stream, nothing synchronises."""
+        check(lib().bnmpc_solve_for_x0(self._h, C.c_void_p(x0_dev.data_ptr()), C.c_void_p(u0_dev.data_ptr()),
+                                       C.c_void_p(status_dev.data_ptr()), 1))
 
     def get_cost(self):
         """acados get_cost(): the NLP objective at the current iterate (LINEAR_LS, stage cost scaled by dt)."""

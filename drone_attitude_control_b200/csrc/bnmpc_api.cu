@@ -550,13 +550,14 @@ int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* stat
     if (!h || !x0) return fail(BNMPC_E_ARG, "NULL argument");
     if (use_device(h)) return BNMPC_E_CUDA;
     const int B = h->batch, nx = h->ops->nx, nu = h->ops->nu;
-    const cudaMemcpyKind in = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    const cudaMemcpyKind out = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (on_device < 0 || on_device > BNMPC_HOST_ASYNC) return fail(BNMPC_E_ARG, "on_device must be 0, 1 or BNMPC_HOST_ASYNC");
+    const cudaMemcpyKind in = on_device == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    const cudaMemcpyKind out = on_device == 1 ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
     if (h->ops->elem_size == 8) {
         CK(cudaMemcpyAsync(h->gs.X0, x0, sizeof(double) * B * nx, in, h->stream));            // lbx_0 = ubx_0 = x0_bar
     } else {
         const double* d;
-        if (int rc = stage_in(h, 0, x0, (size_t)B * nx, on_device, &d)) return rc;
+        if (int rc = stage_in(h, 0, x0, (size_t)B * nx, on_device == 1, &d)) return rc;
         CK(field_xfer(h, F_LBX, 0, const_cast<double*>(d), nx, nx, 1));
     }
     if (int rc = refresh_order(h)) return rc;

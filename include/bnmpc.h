@@ -122,7 +122,12 @@ int bnmpc_solve(void* handle);
 /* ocp_solver.solve_for_x0(x0_bar) of acados_template (used by the reference's dev scripts, src/force_model/ocp.py:162-164)
  * = set(0,'lbx',x0); set(0,'ubx',x0); solve(); get(0,'u'), for all instances in ONE call: x0 AoS [batch][nx] in,
  * u0 AoS [batch][nu] and status int32 [batch] out (either may be NULL).  In FP64 the inputs are copied straight into the
- * solver state and the outputs straight out of it: one kernel launch per call. */
+ * solver state and the outputs straight out of it: one kernel launch per call.
+ * on_device: 0 = host buffers, returns when u0 / status are in host memory; 1 = device buffers, asynchronous on the handle's
+ * stream; BNMPC_HOST_ASYNC (2) = PINNED host buffers, asynchronous - the copies and the solve are enqueued on the handle's
+ * stream and the caller calls bnmpc_synchronize() before reading u0 / status (lets the caller enqueue the upload of the
+ * next step's reference window behind this step's x0 instead of in front of it). */
+#define BNMPC_HOST_ASYNC 2
 int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* status, int on_device);
 /* ocp_solver.get_stats / status: int32 [batch] */
 int bnmpc_get_stats(void* handle, int which, int32_t* out, int on_device);

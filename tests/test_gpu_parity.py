@@ -315,6 +315,18 @@ def test_acados_surface_fields_and_helpers():
     s.solve_for_x0_into(torch.tensor(x0).pin_memory(), uh, sh)
     np.testing.assert_allclose(uh.numpy(), want['u'][:, 0], rtol=0, atol=1e-9)
     assert np.array_equal(sh.numpy(), want['status'])
+    # asynchronous host form (BNMPC_HOST_ASYNC) and the device-buffer form
+    s.reset(); uh.zero_(); sh.fill_(-1)
+    s.solve_for_x0_into(torch.tensor(x0).pin_memory(), uh, sh, wait=False)
+    s.synchronize()
+    np.testing.assert_allclose(uh.numpy(), want['u'][:, 0], rtol=0, atol=1e-9)
+    assert np.array_equal(sh.numpy(), want['status'])
+    s.reset()
+    ud = torch.zeros((B, nu), dtype=torch.float64, device='cuda'); sd = torch.full((B,), -1, dtype=torch.int32, device='cuda')
+    s.solve_for_x0_device(torch.tensor(x0, device='cuda'), ud, sd)
+    s.synchronize()
+    np.testing.assert_allclose(ud.cpu().numpy(), want['u'][:, 0], rtol=0, atol=1e-9)
+    assert np.array_equal(sd.cpu().numpy(), want['status'])
     s32 = pkg.BatchedAcadosOcpSolver('force', batch=B, device=0, precision='fp32')
     s32.set_yref_all(yref)
     u32 = s32.solve_for_x0(x0, fail_on_nonzero_status=False)
