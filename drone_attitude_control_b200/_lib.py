@@ -75,6 +75,7 @@ def lib():
         'bnmpc_gen_circle_table': (C.c_int, [vp, dp, C.c_int, dp]),
         'bnmpc_launch_count': (C.c_int64, [vp]),
         'bnmpc_measure_fma_peak': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
+        'bnmpc_selftest_rcp': (C.c_int, [C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -243,6 +243,33 @@ int fma_peak(double* tflops) {
     return 0;
 }
 
+// rcp_vec against the plain division, bit for bit (bnmpc_selftest_rcp)
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+__global__ void k_rcp_check(long long per_thread, int solver_range, unsigned long long* bad) {
+    uint64_t sd = mix64((uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 0x1234567ULL * (solver_range + 1));
+    unsigned long long nbad = 0;
+    for (long long it = 0; it < per_thread; it++) {
+        double t[6], r[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            sd = mix64(sd + 0x9e3779b97f4a7c15ULL);
+            uint64_t bits = sd;
+            if (solver_range) bits = (sd & 0x000fffffffffffffULL) | ((uint64_t)(1023 - 47 + (int)((sd >> 52) % 68)) << 52);
+            t[i] = __longlong_as_double((long long)bits);
+        }
+        rcp_vec<double, 6>(t, r);
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            const double ref = 1.0 / t[i];
+            if (__double_as_longlong(r[i]) != __double_as_longlong(ref) && !(r[i] != r[i] && ref != ref)) nbad++;
+        }
+    }
+    if (nbad) atomicAdd(bad, nbad);
+}
+
 constexpr int QUEUE_LEN = 1024;
 
 // counter of the work queue for the next launch; the ring is re-zeroed (stream-ordered) when it wraps
@@ -683,6 +710,26 @@ int bnmpc_measure_fma_peak(int device, int precision, double* tflops) {
     if (device < 0 || device >= ndev) return fail(BNMPC_E_ARG, "device index out of range");
     CK(cudaSetDevice(device));
     return precision == BNMPC_FP32 ? fma_peak<float>(tflops) : fma_peak<double>(tflops);
+}
+
+int bnmpc_selftest_rcp(int device, int64_t count, int solver_range, int64_t* mismatches) {
+    if (!mismatches || count < 1) return fail(BNMPC_E_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(BNMPC_E_CUDA, "no CUDA device: libbnmpc has no CPU path");
+    if (device < 0 || device >= ndev) return fail(BNMPC_E_ARG, "device index out of range");
+    CK(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, sizeof(*d)));
+    CK(cudaMemset(d, 0, sizeof(*d)));
+    const int blocks = 592, tpb = 256;
+    const long long per_thread = (count + (long long)blocks * tpb - 1) / ((long long)blocks * tpb);
+    k_rcp_check<<<blocks, tpb>>>(per_thread, solver_range, d);
+    CK(cudaGetLastError());
+    unsigned long long hbad = 0;
+    CK(cudaMemcpy(&hbad, d, sizeof(hbad), cudaMemcpyDeviceToHost));
+    CK(cudaFree(d));
+    *mismatches = (int64_t)hbad;
+    return 0;
 }
 
 int64_t bnmpc_launch_count(void* handle) {

@@ -182,6 +182,13 @@ int bnmpc_closed_loop_state(void* handle, double* cost, double* abs_err, double*
  * vector-pipe figure). */
 int bnmpc_measure_fma_peak(int device, int precision, double* tflops);
 
+/* Device self-test of the reciprocal the solver passes use (bnmpc_core.cuh: rcp_vec, six operands with one range guard):
+ * evaluates it on `count` x 6 pseudo-random operands - solver_range != 0: positive, 1e-14 .. 1e6 (what slacks look like);
+ * 0: all bit patterns, including zeros, subnormals, infinities and NaNs - and counts the results whose bits differ from
+ * the IEEE division 1.0 / t (NaN == NaN).  The solver's parity claim needs *mismatches == 0.  No reference counterpart:
+ * acados divides on the CPU. */
+int bnmpc_selftest_rcp(int device, int64_t count, int solver_range, int64_t* mismatches);
+
 /* number of kernels this library has launched on the handle since creation */
 int64_t bnmpc_launch_count(void* handle);
 const char* bnmpc_last_error(void);

@@ -207,11 +207,12 @@ def _fast_loop_inputs(B, S, seed, mass_sigma=0.0):
     return refs, x0, noise, pc, pp
 
 
-@pytest.mark.parametrize('model,B', [('force', 4096), ('jerk', 16384)])
+@pytest.mark.parametrize('model,B', [('force', 4096), ('force', 6144), ('jerk', 16384)])
 def test_full_size_batches_match_oracle_on_a_subset(model, B):
     """BASELINE batch sizes (config 2: 4096 force drones, config 3: 16384 jerk drones; plant mass perturbed as in
     config 4).  The instances are independent, so the oracle is run on a subset - every instance that ended a step with
-    a non-zero status plus random ones - with exactly the inputs those instances had in the big batch."""
+    a non-zero status plus random ones - with exactly the inputs those instances had in the big batch.  (6144 force and
+    16384 jerk drones are more than two per resident warp: those runs go through the longest-first work-queue order.)"""
     S = 30
     refs, x0, noise, pc, pp = _fast_loop_inputs(B, S, seed=77, mass_sigma=0.05)
     got, _ = _run_loop(model, refs, x0, noise, pc, pp, S)
@@ -465,3 +466,14 @@ def test_results_surface_for_plotting_and_statistics(tmp_path):
     st = sr.batch_statistics(res)
     assert st['n'] == B and st['status_hist'][0] == B * S and st['cost']['p5'] <= st['cost']['p50'] <= st['cost']['p95'] <= st['cost']['max']
     assert abs(st['aed']['mean'] - got['aed'].mean()) < 1e-15 and st['qp_iter']['max'] == got['qp_iter'].max()
+
+
+def test_device_reciprocal_is_bit_identical_to_ieee_division():
+    """The passes compute their six reciprocals with rcp_vec (compiler's fast-path sequence, one range guard); the parity
+    claim needs it to return the bits of 1.0 / t for every operand, in and out of the fast path's range."""
+    import ctypes as C
+    from drone_attitude_control_b200 import _lib
+    for solver_range in (1, 0):
+        bad = C.c_int64(-1)
+        _lib.check(_lib.lib().bnmpc_selftest_rcp(0, 200_000_000, solver_range, C.byref(bad)))
+        assert bad.value == 0, (solver_range, bad.value)
