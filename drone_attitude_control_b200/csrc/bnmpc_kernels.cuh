@@ -2,26 +2,27 @@
 // Each model_*.cu instantiates BNMPC_DEFINE_MODEL_OPS for one generated model (both precisions); bnmpc_api.cu only
 // sees the ModelOps table, so the heavy templates compile in parallel translation units.
 //
-// Launch shape: ONE PERSISTENT CTA per SM with as many warps as the on-chip memories hold instances (14 for the force
-// model at N = 30); every warp pulls OCP instances from an atomic work queue and solves them one at a time (instance
-// solve lengths differ by 4x, so the queue balances itself).  Warps of a CTA never synchronise during the solves; the
-// CTA exists because of tensor memory:
+// Launch shape: ONE PERSISTENT CTA per SM with as many warps as the on-chip memories hold instances (16 for the force
+// model, 12 for the jerk model at N = 30); every warp pulls OCP instances from an atomic work queue and solves them one
+// at a time (instance solve lengths differ by 4x, so the queue balances itself).  Warps of a CTA never synchronise
+// during the solves; the CTA exists because of tensor memory:
 //
 //   * shared memory holds the part of an instance's working set that the Riccati sweeps and neighbouring stages touch
-//     (SmLayout<M,false>: 31 doubles per (stage, block) item for the force model, 15.4 KB per instance);
-//   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t: 15 doubles per item).  A warp
-//     owns the 32 TMEM lanes of its quarter (warp id mod 4) in the column group of its warp quad (warp id / 4); lane l
-//     keeps the records of its items in consecutive columns and moves a whole record with one tcgen05.ld / tcgen05.st
-//     (.32x32b.x32).  TMEM is used purely as a software-managed,
+//     (SmLayout: 27 doubles per (stage, block) item for the force model, 13.4 KB per instance);
+//   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t: 15 doubles per item, plus the
+//     dynamics offset b_k where the record has room).  A warp owns the 32 TMEM lanes of its quarter (warp id mod 4) in
+//     the column group of its warp quad (warp id / 4); lane l keeps the records of its items in consecutive columns and
+//     moves a whole record with one tcgen05.ld / tcgen05.st (.32x32b.x32).  TMEM is used purely as a software-managed,
 //     lane-private scratchpad - no tcgen05.mma is involved: these are 3x3 / 4x4 FP64 problems.
 //
-// This raises the instances in flight per SM from 8 to 12.  Measured (force model, 65536 instances, M solves/s): ONE CTA of
-// 12 warps at 168 registers 7.20; three CTAs of 4 warps at 168 registers 6.20; one CTA at 128 registers with 8 / 10 / 11 /
-// 12 / 13 / 14 warps 5.03 / 5.08 / 5.58 / 6.57 / 5.87 / 6.04 - only whole multiples of the four SM sub-partitions pay, and
-// registers beat a 4th warp per sub-partition.  The launch bound is therefore per model: the largest multiple of four
-// warps (at most BNMPC_MAX_WARPS = 12) whose instances fit shared memory at the reference horizon N = 30 - 12 for the
-// force model (168 registers), 8 for the jerk model (255 registers).  The warps actually launched per CTA follow from the
-// horizon of the handle and the tensor-memory columns (cta_shape below).
+// Measured (force model, 65536 instances, M solves/s): three CTAs of 4 warps at 168 registers 6.20; ONE CTA of 12 warps
+// at 168 registers 7.20; one CTA at 128 registers with 8 / 10 / 11 / 12 / 13 / 14 warps 5.03 / 5.08 / 5.58 / 6.57 / 5.87 /
+// 6.04 - only whole multiples of the four SM sub-partitions pay.  With the block constants bound per lane the force kernel
+// needs 124-128 registers, and with Phi_k formed in the scans 16 instances fit shared memory: 16 warps 8.54 vs 12 warps
+// 7.63.  The launch bound is per model (LaunchShape): the largest multiple of four warps (at most BNMPC_MAX_WARPS = 16)
+// whose instances fit shared memory at the reference horizon N = 30 - 16 for the force model (128 registers), 12 for the
+// jerk model (168 registers), 8 for the dense 4-state models (255 registers).  The warps actually launched per CTA
+// follow from the horizon of the handle and the tensor-memory columns (cta_shape below).
 #pragma once
 #include <cuda_runtime.h>
 #include <string.h>
