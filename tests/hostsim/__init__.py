@@ -18,7 +18,7 @@ FP64, FP32 = 0, 1
 
 class Opts(C.Structure):
     _fields_ = [('N', C.c_int), ('erk_stages', C.c_int), ('sqp_max_iter', C.c_int), ('qp_max_iter', C.c_int), ('rti', C.c_int),
-                ('sim_erk_stages', C.c_int), ('sim_substeps', C.c_int), ('smem_stride', C.c_int),
+                ('sim_erk_stages', C.c_int), ('sim_substeps', C.c_int), ('smem_stride', C.c_int), ('order', C.c_void_p),
                 ('dt', C.c_double), ('sim_dt', C.c_double),
                 ('W', C.c_double * 12), ('W_e', C.c_double * 8), ('lbx', C.c_double * 8), ('ubx', C.c_double * 8),
                 ('lbu', C.c_double * 4), ('ubu', C.c_double * 4), ('tol', C.c_double * 4), ('qp_tol', C.c_double * 4),
