@@ -477,3 +477,43 @@ def test_device_reciprocal_is_bit_identical_to_ieee_division():
         bad = C.c_int64(-1)
         _lib.check(_lib.lib().bnmpc_selftest_rcp(0, 200_000_000, solver_range, C.byref(bad)))
         assert bad.value == 0, (solver_range, bad.value)
+
+
+def test_results_do_not_depend_on_the_launch_shape(monkeypatch):
+    """Warps per SM, the longest-first queue order and which warp solves which instance only move work in time: the
+    outputs are bit-identical for every setting of the tuning knobs."""
+    B, S = 700, 12
+    refs, x0, noise, pc, pp = _fast_loop_inputs(B, S, seed=5, mass_sigma=0.05)
+    base, _ = _run_loop('force', refs, x0, noise, pc, pp, S)
+    for env in ({'BNMPC_WARPS_PER_SM': '1'}, {'BNMPC_WARPS_PER_SM': '5'}, {'BNMPC_WARPS_PER_SM': '2', 'BNMPC_NO_ORDER': '1'}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got, _ = _run_loop('force', refs, x0, noise, pc, pp, S)     # 700 drones on 148 x 1 / 2 warps: queue + ordering active
+        for k in ('Xsim', 'U_ctrl', 'U_plant', 'a', 'cost', 'status', 'qp_iter'):
+            assert np.array_equal(got[k], base[k]), (env, k)
+        for k in env:
+            monkeypatch.delenv(k)
+
+
+def test_work_queue_ring_wraps():
+    """Every launch takes a fresh counter from a ring of 1024; the ring is re-zeroed (stream-ordered) when it wraps."""
+    B, N = 6, 5
+    om = MODEL_ID['force']
+    x0, yref = random_solve_inputs(om, B, seed=8, N=N)
+    oo = co.default_opts(om); oo.N = N
+    want = co.solve_batch(oo, x0, yref, np.repeat(P_NOM[None], B, 0))
+    s = pkg.BatchedAcadosOcpSolver('force', batch=B, device=0, N_horizon=N)
+    s.set_yref_all(yref)
+    x0t = torch.tensor(x0, device='cuda')
+    ud = torch.zeros((B, 2), dtype=torch.float64, device='cuda'); sd = torch.zeros(B, dtype=torch.int32, device='cuda')
+    for i in range(2300):                       # > 2 wraps
+        if i % 700 == 0:
+            s.reset()                           # cold start again: the next solve must reproduce the oracle's cold solve
+            s.solve_for_x0_device(x0t, ud, sd)
+            s.synchronize()
+            np.testing.assert_allclose(ud.cpu().numpy(), want['u'][:, 0], rtol=0, atol=1e-9)
+            assert np.array_equal(sd.cpu().numpy(), want['status'])
+        else:
+            s.solve_for_x0_device(x0t, ud, sd)
+    s.synchronize()
+    assert s.launch_count() >= 2300
