@@ -8,9 +8,9 @@
 // during the solves; the CTA exists because of tensor memory:
 //
 //   * shared memory holds the part of an instance's working set that the Riccati sweeps and neighbouring stages touch
-//     (SmLayout: 27 doubles per (stage, block) item for the force model, 13.4 KB per instance);
-//   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t: 15 doubles per item, plus the
-//     dynamics offset b_k where the record has room).  A warp owns the 32 TMEM lanes of its quarter (warp id mod 4) in
+//     (SmLayout: 25 doubles per (stage, block) item for the force model, 12.4 KB per instance);
+//   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t and their reciprocals, plus the
+//     dynamics offset b_k where the record has room: 23 doubles per item for the force model).  A warp owns the 32 TMEM lanes of its quarter (warp id mod 4) in
 //     the column group of its warp quad (warp id / 4); lane l keeps the records of its items in consecutive columns and
 //     moves a whole record with one tcgen05.ld / tcgen05.st (.32x32b.x32).  TMEM is used purely as a software-managed,
 //     lane-private scratchpad - no tcgen05.mma is involved: these are 3x3 / 4x4 FP64 problems.
@@ -94,9 +94,11 @@ struct TmemPriv {
     static constexpr bool IN_SMEM = false;
     static constexpr int s = M::NXB + M::NUB, n = M::NXB;
     static constexpr int WPE = (int)sizeof(T) / 4;                 // 32-bit words per element
-    static constexpr int CH = (5 * s * WPE + 31) / 32;             // .x32 chunks per record (q, lam, t)
-    static constexpr bool QB_PRIV = (5 * s + n) * WPE <= CH * 32;  // room for the dynamics offset b_k in the same chunks
-    static constexpr int NE = 5 * s + (QB_PRIV ? n : 0);           // elements of a record: q, lam, t [, b]
+    static constexpr bool TI_PRIV = true;                          // the reciprocals 1/t travel with the record (7 s elements)
+    static constexpr int CH = (7 * s * WPE + 31) / 32;             // .x32 chunks per record (q, lam, t, 1/t)
+    static constexpr bool QB_PRIV = (7 * s + n) * WPE <= CH * 32;  // room for the dynamics offset b_k in the same chunks
+    static constexpr int NQ = QB_PRIV ? n : 0;
+    static constexpr int NE = 7 * s + NQ;                          // elements of a record: q, lam, t [, b], 1/t
     static constexpr int CPR = CH * 32;                            // columns per round of items
     uint32_t base;                                                 // lane quarter of this warp | first column
 
@@ -131,6 +133,8 @@ struct TmemPriv {
 #pragma unroll
             for (int v = 0; v < n; v++) r.qb[v] = e[5 * s + v];
         }
+#pragma unroll
+        for (int v = 0; v < 2 * s; v++) r.ti[v] = e[5 * s + NQ + v];
     }
     __device__ __forceinline__ void store(T*, int rd, int, bool, const PrivRec<T, s, n>& r) const {
         T e[NE];
@@ -142,6 +146,8 @@ struct TmemPriv {
 #pragma unroll
             for (int v = 0; v < n; v++) e[5 * s + v] = r.qb[v];
         }
+#pragma unroll
+        for (int v = 0; v < 2 * s; v++) e[5 * s + NQ + v] = r.ti[v];
         uint32_t w[CH * 32];
         __syncwarp();
 #pragma unroll
