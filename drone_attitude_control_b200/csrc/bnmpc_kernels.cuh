@@ -8,7 +8,7 @@
 // during the solves; the CTA exists because of tensor memory:
 //
 //   * shared memory holds the part of an instance's working set that the Riccati sweeps and neighbouring stages touch
-//     (SmLayout: 25 doubles per (stage, block) item for the force model, 12.4 KB per instance);
+//     (SmLayout: 29 doubles per (stage, block) item for the force model, 14.4 KB per instance);
 //   * TENSOR MEMORY holds the lane-private part (gradient q, multipliers lam, slacks t and their reciprocals, plus the
 //     dynamics offset b_k where the record has room: 23 doubles per item for the force model).  A warp owns the 32 TMEM lanes of its quarter (warp id mod 4) in
 //     the column group of its warp quad (warp id / 4); lane l keeps the records of its items in consecutive columns and
