@@ -98,7 +98,12 @@ struct TmemPriv {
     static constexpr int CH = (7 * s * WPE + 31) / 32;             // .x32 chunks per record (q, lam, t, 1/t)
     static constexpr bool QB_PRIV = (7 * s + n) * WPE <= CH * 32;  // room for the dynamics offset b_k in the same chunks
     static constexpr int NQ = QB_PRIV ? n : 0;
-    static constexpr int NE = 7 * s + NQ;                          // elements of a record: q, lam, t [, b], 1/t
+    // what else the chunks have room for: the bound residuals rd and the stationarity residual rg of the predictor pass
+    static constexpr bool RD_PRIV = (7 * s + NQ + 2 * s) * WPE <= CH * 32;
+    static constexpr int NRD = RD_PRIV ? 2 * s : 0;
+    static constexpr bool RG_PRIV = RD_PRIV && (7 * s + NQ + NRD + s) * WPE <= CH * 32;
+    static constexpr int NRG = RG_PRIV ? s : 0;
+    static constexpr int NE = 7 * s + NQ + NRD + NRG;              // elements of a record: q, lam, t [, b], 1/t [, rd] [, rg]
     static constexpr int CPR = CH * 32;                            // columns per round of items
     uint32_t base;                                                 // lane quarter of this warp | first column
 
@@ -135,6 +140,14 @@ struct TmemPriv {
         }
 #pragma unroll
         for (int v = 0; v < 2 * s; v++) r.ti[v] = e[5 * s + NQ + v];
+        if constexpr (RD_PRIV) {
+#pragma unroll
+            for (int v = 0; v < 2 * s; v++) r.rd[v] = e[7 * s + NQ + v];
+        }
+        if constexpr (RG_PRIV) {
+#pragma unroll
+            for (int v = 0; v < s; v++) r.rg[v] = e[7 * s + NQ + NRD + v];
+        }
     }
     __device__ __forceinline__ void store(T*, int rd, int, bool, const PrivRec<T, s, n>& r) const {
         T e[NE];
@@ -148,6 +161,14 @@ struct TmemPriv {
         }
 #pragma unroll
         for (int v = 0; v < 2 * s; v++) e[5 * s + NQ + v] = r.ti[v];
+        if constexpr (RD_PRIV) {
+#pragma unroll
+            for (int v = 0; v < 2 * s; v++) e[7 * s + NQ + v] = r.rd[v];
+        }
+        if constexpr (RG_PRIV) {
+#pragma unroll
+            for (int v = 0; v < s; v++) e[7 * s + NQ + NRD + v] = r.rg[v];
+        }
         uint32_t w[CH * 32];
         __syncwarp();
 #pragma unroll
