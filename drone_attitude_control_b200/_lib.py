@@ -29,9 +29,11 @@ class Config(C.Structure):
 class ClosedLoopArgs(C.Structure):
     """struct bnmpc_closed_loop_args"""
     _fields_ = [('n_steps', C.c_int32), ('first_step', C.c_int32), ('ref_rows', C.c_int32), ('ref_shared', C.c_int32),
-                ('log_stride', C.c_int32), ('reserved', C.c_int32),
+                ('log_stride', C.c_int32), ('steps_per_launch', C.c_int32),
                 ('ref', C.c_void_p), ('noise', C.c_void_p), ('Xsim', C.c_void_p), ('U_plant', C.c_void_p), ('U_ctrl', C.c_void_p),
-                ('a_log', C.c_void_p), ('status', C.c_void_p), ('qp_iter', C.c_void_p)]
+                ('a_log', C.c_void_p), ('status', C.c_void_p), ('qp_iter', C.c_void_p),
+                ('noise_philox', C.c_int32), ('reserved', C.c_int32), ('noise_seed', C.c_uint64), ('noise_std', C.c_double),
+                ('first_instance', C.c_int64)]
 
 
 class BnmpcError(RuntimeError):
@@ -72,8 +74,11 @@ def lib():
         'bnmpc_closed_loop_init': (C.c_int, [vp, dp, dp, dp]),
         'bnmpc_closed_loop_run': (C.c_int, [vp, C.POINTER(ClosedLoopArgs)]),
         'bnmpc_closed_loop_state': (C.c_int, [vp, dp, dp, dp, dp]),
+        'bnmpc_closed_loop_failures': (C.c_int, [vp, vp, C.c_int]),
+        'bnmpc_philox_noise': (C.c_int, [vp, C.c_uint64, C.c_double, C.c_int64, C.c_int, C.c_int, dp]),
         'bnmpc_gen_circle_table': (C.c_int, [vp, dp, C.c_int, dp]),
         'bnmpc_launch_count': (C.c_int64, [vp]),
+        'bnmpc_debug_profile': (C.c_int, [vp, vp, C.c_int]),
         'bnmpc_measure_fma_peak': (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
         'bnmpc_selftest_rcp': (C.c_int, [C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int64)]),
     }

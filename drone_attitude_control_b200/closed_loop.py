@@ -29,6 +29,15 @@ class CircleRef:
         self.n = int(n)
 
 
+class PhiloxNoise:
+    """Plant noise drawn on the device: eps(instance, step) = std * N(0, 1) from Philox4x32-10 keyed by `seed` with the
+    counter (first_instance + i, step) - the scalar np.random.normal(0, noise) of the reference's simulate_next_x
+    (src/force_model/ocp.py:114-115), without a [steps, batch] array and independent of how the batch is sharded."""
+
+    def __init__(self, seed=2026, std=p.noise, first_instance=0):
+        self.seed, self.std, self.first_instance = int(seed), float(std), int(first_instance)
+
+
 class BatchedClosedLoop:
     def __init__(self, model='force', batch=1, device=0, precision='fp64', N_horizon=None, rti=False, **overrides):
         self.solver = BatchedAcadosOcpSolver(model, batch=batch, device=device, precision=precision,
@@ -67,7 +76,8 @@ class BatchedClosedLoop:
                 self.ref_layout, self.ref_rows = 2, int(self.ref.shape[1])
         self.n_steps = int(n_steps if n_steps is not None else self.ref_rows - self.N)
         assert self.ref_rows >= self.n_steps + self.N
-        self.noise = self._dev(noise)[:self.n_steps].contiguous() if noise is not None else None
+        self.philox = noise if isinstance(noise, PhiloxNoise) else None
+        self.noise = self._dev(noise)[:self.n_steps].contiguous() if noise is not None and self.philox is None else None
         assert self.noise is None or tuple(self.noise.shape) == (self.n_steps, B)
         self.p_ctrl = self._dev(p_ctrl, (2, B)) if p_ctrl is not None else None
         self.p_plant = self._dev(p_plant, (2, B)) if p_plant is not None else None
@@ -91,14 +101,28 @@ class BatchedClosedLoop:
         check(lib().bnmpc_gen_circle_table(self.solver.handle, C.c_void_p(self.ref.data_ptr()), rows, C.c_void_p(out.data_ptr())))
         return out
 
-    def run(self, n_steps=None):
-        """Advance `n_steps` control steps (default: the rest); one kernel launch per step."""
+    def noise_array(self):
+        """The draws of the PhiloxNoise of this loop as an array [n_steps, B] (what the fused loop adds, bit for bit)."""
+        assert self.philox is not None
+        out = torch.empty((self.n_steps, self.batch), dtype=torch.float64, device=self.device)
+        check(lib().bnmpc_philox_noise(self.solver.handle, self.philox.seed, self.philox.std, self.philox.first_instance, 0,
+                                       self.n_steps, C.c_void_p(out.data_ptr())))
+        return out
+
+    def run(self, n_steps=None, steps_per_launch=1):
+        """Advance `n_steps` control steps (default: the rest).  steps_per_launch = 1: one kernel launch per control step
+        (every launch ends with all drones at the same step - the latency path).  steps_per_launch = k > 1: up to k control
+        steps per launch; a drone keeps its working set on chip for a chunk of consecutive steps and drones advance
+        independently inside the launch (Monte-Carlo throughput path, same results)."""
         n = self.n_steps - self.step if n_steps is None else int(n_steps)
         a = ClosedLoopArgs()
         a.n_steps, a.first_step, a.ref_rows = n, self.step, self.ref_rows
         a.ref_shared, a.log_stride = self.ref_layout, self.n_steps
+        a.steps_per_launch = int(steps_per_launch)
         a.ref = self.ref.data_ptr()
         a.noise = self.noise.data_ptr() if self.noise is not None else None
+        if self.philox is not None:
+            a.noise_philox, a.noise_seed, a.noise_std, a.first_instance = 1, self.philox.seed, self.philox.std, self.philox.first_instance
         L = self._logs
         if L:
             a.Xsim, a.U_plant, a.U_ctrl, a.a_log = (L[k].data_ptr() for k in ('Xsim', 'U_plant', 'U_ctrl', 'a'))
@@ -115,20 +139,28 @@ class BatchedClosedLoop:
         check(lib().bnmpc_closed_loop_state(self.solver.handle, *(C.c_void_p(t.data_ptr()) for t in (cost, err, x, acc))))
         return cost, err, x, acc
 
+    def failures(self):
+        """int32 [B]: control steps so far whose solve returned a non-zero status (the reference raises on the first one;
+        the fused loop keeps stepping and counts)."""
+        out = torch.empty(self.batch, dtype=torch.int32, device=self.device)
+        check(lib().bnmpc_closed_loop_failures(self.solver.handle, C.c_void_p(out.data_ptr()), 1))
+        return out
+
     def results(self):
         """Per-instance outputs in the reference's shapes: cost [B], AvgEucDist [B] (calc_aed over the steps run), and the
         logs Xsim [B, S+1, 4], a [B, S, 2], U_opt_plant [B, S, 2] (+ U_ctrl, status, qp_iter)."""
         cost, err, _, _ = self.state()
-        out = dict(cost=cost, aed=err / (2.0 * max(self.step, 1)))
+        out = dict(cost=cost, aed=err / (2.0 * max(self.step, 1)), failures=self.failures())
         for k, v in self._logs.items():
             out[k] = v.permute(2, 0, 1) if v.dim() == 3 else v.t()
         return out
 
 
-def follow_trajectory_batched(model, ref, x0, noise=None, p_ctrl=None, p_plant=None, n_steps=None, device=0, precision='fp64', **kw):
+def follow_trajectory_batched(model, ref, x0, noise=None, p_ctrl=None, p_plant=None, n_steps=None, device=0, precision='fp64',
+                              steps_per_launch=1, **kw):
     """follow_trajectory for B drones in one call; returns the dict of BatchedClosedLoop.results()."""
     x0 = torch.as_tensor(x0, dtype=torch.float64)
     loop = BatchedClosedLoop(model, batch=x0.shape[1], device=device, precision=precision, **kw)
     loop.init(x0, ref, noise=noise, p_ctrl=p_ctrl, p_plant=p_plant, n_steps=n_steps)
-    loop.run()
+    loop.run(steps_per_launch=steps_per_launch)
     return loop.results()

@@ -42,6 +42,12 @@ struct Handle {
     // closed-loop state, stride Bp
     size_t Bp;
     double *xs, *acc, *cost, *abs_err, *p_plant;
+    int32_t* fail_count;           // [batch] closed-loop steps with a non-zero solver status since closed_loop_init
+    int* next_step;                // [batch] next control step of every instance (orders the step chunks of a multi-step launch)
+    int loop_kernel;               // 0: one warp per instance with a work queue (k_loop_step), 1: slotted lockstep (k_loop_ls)
+    int chunk_override;            // BNMPC_CHUNK: steps per queue ticket of a multi-step launch (0 = automatic)
+    int ls_generation;             // BNMPC_LS_GENERATION: see LoopArgs::ls_generation
+    long long* prof; int prof_cap; // bnmpc_debug_profile
     int64_t launches;
 };
 
@@ -175,10 +181,23 @@ __global__ void k_circle_table(int B, int rows, int n, const double* prm, double
     out[idx] = circle_ref(prm + (size_t)inst * 4, row, col, n);
 }
 
+__global__ void k_philox_noise(int B, int n_steps, int first_step, unsigned long long seed, double std_, long long inst0, double* out) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * n_steps) return;
+    const int i = (int)(idx % B), s = (int)(idx / B);
+    out[idx] = std_ * philox_normal(seed, inst0 + i, first_step + s);
+}
+
+__global__ void k_fill_int(int n, int v, int* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
 __global__ void k_loop_init(int B, size_t Bp, const double* x0, const double* p_ctrl, const double* p_plant, double* xs, double* acc,
-                            double* cost, double* abs_err, double* pp) {
+                            double* cost, double* abs_err, double* pp, int32_t* fail_count) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
+    fail_count[i] = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) xs[(size_t)j * Bp + i] = x0[(size_t)j * B + i];
     acc[i] = 0.0;                                             // jerk controller.py:23  a_i = [0, g]
@@ -409,6 +428,8 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     ok = ok && cudaMalloc(&h->xs, sizeof(double) * 11 * h->Bp) == cudaSuccess;
     ok = ok && cudaMalloc(&h->gs.U0, sizeof(double) * (size_t)batch * ops->nu) == cudaSuccess;
     ok = ok && cudaMalloc(&h->order, sizeof(int) * (size_t)batch) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->fail_count, sizeof(int32_t) * (size_t)batch) == cudaSuccess;
+    ok = ok && cudaMalloc(&h->next_step, sizeof(int) * (size_t)batch) == cudaSuccess;
     if (!ok) {
         const std::string msg = std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError());
         bnmpc_destroy(h);
@@ -446,6 +467,12 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     CKH(cudaMemsetAsync(h->gs_base, 0, h->gs_bytes, h->stream));
     CKH(cudaMemsetAsync(h->ints, 0, sizeof(int32_t) * 4 * batch, h->stream));
     CKH(cudaMemsetAsync(h->xs, 0, sizeof(double) * 11 * h->Bp, h->stream));
+    CKH(cudaMemsetAsync(h->fail_count, 0, sizeof(int32_t) * batch, h->stream));
+    CKH(cudaMemsetAsync(h->next_step, 0, sizeof(int) * batch, h->stream));
+    h->loop_kernel = 0;
+    if (const char* e = getenv("BNMPC_LOOP_KERNEL")) h->loop_kernel = (strcmp(e, "ls") == 0) ? 1 : 0;
+    if (const char* e = getenv("BNMPC_CHUNK")) h->chunk_override = atoi(e);
+    if (const char* e = getenv("BNMPC_LS_GENERATION")) h->ls_generation = atoi(e);
     // nominal parameters p = (mass, g) for every instance (reference src/params.py:37,42)
     double* pnom = nullptr;
     const double pn[2] = {0.03277, 9.81};
@@ -466,6 +493,8 @@ int bnmpc_destroy(void* handle) {
     if (h->ints) cudaFree(h->ints);
     if (h->queue) cudaFree(h->queue);
     if (h->order) cudaFree(h->order);
+    if (h->fail_count) cudaFree(h->fail_count);
+    if (h->next_step) cudaFree(h->next_step);
     if (h->xs) cudaFree(h->xs);
     if (h->gs.U0) cudaFree(h->gs.U0);
     for (int i = 0; i < 4; i++) if (h->stage[i]) cudaFree(h->stage[i]);
@@ -547,8 +576,7 @@ int bnmpc_set_yref_all(void* handle, const double* value, int on_device) {
     {
         const size_t tot = per * h->batch;
         const int grid = (int)((tot + 127) / 128);
-        if (h->ops->elem_size == 8) k_yref_all<double><<<grid, 128, 0, h->stream>>>(gs_cast<double>(h->gs), h->ops->nx, h->ops->nu, h->ops->np, d);
-        else k_yref_all<float><<<grid, 128, 0, h->stream>>>(gs_cast<float>(h->gs), h->ops->nx, h->ops->nu, h->ops->np, d);
+        k_yref_all<float><<<grid, 128, 0, h->stream>>>(gs_cast<float>(h->gs), h->ops->nx, h->ops->nu, h->ops->np, d);   // (FP64 returned above)
         CK(cudaGetLastError()); h->launches++;
     }
     return 0;
@@ -641,7 +669,7 @@ int bnmpc_closed_loop_init(void* handle, const double* x0, const double* p_ctrl,
     if (use_device(h)) return BNMPC_E_CUDA;
     if (int rc = reset_iterate(h)) return rc;
     const int B = h->batch;
-    k_loop_init<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->Bp, x0, p_ctrl, p_plant, h->xs, h->acc, h->cost, h->abs_err, h->p_plant);
+    k_loop_init<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->Bp, x0, p_ctrl, p_plant, h->xs, h->acc, h->cost, h->abs_err, h->p_plant, h->fail_count);
     CK(cudaGetLastError()); h->launches++;
     if (p_ctrl) {
         if (h->ops->elem_size == 8) k_par_from_bm<double><<<(B + 127) / 128, 128, 0, h->stream>>>(gs_cast<double>(h->gs), h->ops->np, p_ctrl);
@@ -661,6 +689,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     if (!h || !a || !a->ref) return fail(BNMPC_E_ARG, "NULL argument");
     if (a->n_steps < 0 || a->first_step < 0) return fail(BNMPC_E_ARG, "negative step count");
     if (a->first_step + a->n_steps + h->cfg.horizon > a->ref_rows) return fail(BNMPC_E_ARG, "ref has too few rows for first_step + n_steps + N");
+    if (a->noise_philox && a->noise) return fail(BNMPC_E_ARG, "noise array and noise_philox are exclusive");
     const bool logs = a->noise || a->Xsim || a->U_plant || a->U_ctrl || a->a_log || a->status || a->qp_iter;
     if (logs && a->log_stride < a->first_step + a->n_steps) return fail(BNMPC_E_ARG, "log_stride too small");
     if (use_device(h)) return BNMPC_E_CUDA;
@@ -671,14 +700,69 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     la.kind = h->ops->kind; la.ref_layout = a->ref_shared; la.ref_rows = a->ref_rows; la.log_stride = a->log_stride; la.batch = h->batch; la.Bp = h->Bp;
     la.ref = a->ref; la.noise = a->noise; la.Xsim = a->Xsim; la.U_plant = a->U_plant; la.U_ctrl = a->U_ctrl; la.a_log = a->a_log;
     la.status = a->status; la.qp_iter = a->qp_iter;
+    la.noise_philox = a->noise_philox; la.noise_seed = a->noise_seed; la.noise_std = a->noise_std; la.inst0 = a->first_instance;
     la.xs = h->xs; la.acc = h->acc; la.cost = h->cost; la.abs_err = h->abs_err; la.p_plant = h->p_plant;
-    for (int s = 0; s < a->n_steps; s++) {
-        la.step = a->first_step + s;
+    la.fail_count = h->fail_count; la.next_step = h->next_step;
+    la.ls_generation = h->ls_generation; la.prof = h->prof; la.prof_cap = h->prof_cap;
+    const int spl = a->steps_per_launch > 1 ? a->steps_per_launch : 1;
+    const int slots = h->ctas * h->warps;
+    for (int s = 0; s < a->n_steps;) {
+        const int ns = (a->n_steps - s) < spl ? (a->n_steps - s) : spl;
+        la.step = a->first_step + s; la.n_steps = ns;
         if (int rc = refresh_order(h)) return rc;
         int* q;
         if (int rc = next_queue(h, &q)) return rc;
-        CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream)); h->launches++;
+        if (ns == 1 && h->loop_kernel == 0) {
+            la.chunk = 1;
+            CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream)); h->launches++;
+        } else {
+            const bool ls = h->loop_kernel == 1;
+            // steps of an instance per queue ticket: long enough to amortise the load of the persistent state, short enough
+            // for ~32 tickets per resident warp so that the launch ends without a tail; one ticket per instance when every
+            // instance has a warp of its own anyway
+            long long chunk = h->batch <= slots ? ns : ((long long)h->batch * ns) / (32LL * slots);
+            if (h->chunk_override > 0) chunk = h->chunk_override;
+            if (chunk < 1) chunk = 1;
+            if (chunk > ns) chunk = ns;
+            la.chunk = (int)chunk;
+            if (chunk < ns) {
+                k_fill_int<<<(h->batch + 255) / 256, 256, 0, h->stream>>>(h->batch, la.step, h->next_step);
+                CK(cudaGetLastError()); h->launches++;
+            }
+            if (ls) CK(h->ops->loop_ls(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream));
+            else CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream));
+            h->launches++;
+        }
+        s += ns;
     }
+    return 0;
+}
+
+int bnmpc_philox_noise(void* handle, uint64_t seed, double noise_std, int64_t first_instance, int first_step, int n_steps, double* out) {
+    Handle* h = (Handle*)handle;
+    if (!h || !out) return fail(BNMPC_E_ARG, "NULL argument");
+    if (n_steps < 0 || first_step < 0) return fail(BNMPC_E_ARG, "negative step count");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const size_t tot = (size_t)h->batch * n_steps;
+    if (tot == 0) return 0;
+    k_philox_noise<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->batch, n_steps, first_step, seed, noise_std, first_instance, out);
+    CK(cudaGetLastError()); h->launches++;
+    return 0;
+}
+
+int bnmpc_debug_profile(void* handle, long long* buf, int cap) {
+    Handle* h = (Handle*)handle;
+    if (!h) return fail(BNMPC_E_ARG, "NULL handle");
+    h->prof = buf; h->prof_cap = buf ? cap : 0;
+    return 0;
+}
+
+int bnmpc_closed_loop_failures(void* handle, int32_t* out, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !out) return fail(BNMPC_E_ARG, "NULL argument");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    CK(cudaMemcpyAsync(out, h->fail_count, sizeof(int32_t) * h->batch, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    if (!on_device) CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -27,7 +27,7 @@
 #include <cuda_runtime.h>
 #include <string.h>
 
-#include "bnmpc_loop.cuh"
+#include "bnmpc_lockstep.cuh"
 
 #ifndef BNMPC_MAX_WARPS
 #define BNMPC_MAX_WARPS 16       // warps of the one resident CTA per SM the register allocator leaves room for (launch bound)
@@ -54,6 +54,8 @@ struct ModelOps {
     int (*tmem_cols)(int N, int warps);                             // tensor-memory columns a CTA of `warps` allocates (0 = too many)
     cudaError_t (*solve)(const GsAny&, const Opts&, int ctas, int warps, int* queue, cudaStream_t);
     cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
+    // slotted lockstep schedule (bnmpc_lockstep.cuh): LoopArgs::n_steps control steps per launch, tickets of LoopArgs::chunk steps
+    cudaError_t (*loop_ls)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
     cudaError_t (*cta_shape)(int N, int* warps);                    // warps per CTA (= instances in flight per SM), 0 = does not fit
 };
 
@@ -233,6 +235,31 @@ __device__ __forceinline__ int next_instance(int* queue, const int* order, int B
     return __shfl_sync(0xffffffffu, i, 0);
 }
 
+struct DevTickets {
+    int* queue; int* next_step;
+    __device__ __forceinline__ int take() const {
+        int i = 0;
+        if ((threadIdx.x & 31) == 0) i = atomicAdd(queue, 1);
+        return __shfl_sync(0xffffffffu, i, 0);
+    }
+    __device__ __forceinline__ bool ready(int inst, int step) const {
+        int v = 0;
+        if ((threadIdx.x & 31) == 0) v = *(volatile int*)(next_step + inst);
+        v = __shfl_sync(0xffffffffu, v, 0);
+        if (v != step) return false;
+        __threadfence();
+        return true;
+    }
+    __device__ __forceinline__ void wait(int inst, int step) const {      // free-running warps only (never inside a CTA-wide schedule)
+        while (!ready(inst, step)) __nanosleep(200);
+    }
+    __device__ __forceinline__ void publish(int inst, int next) const {
+        __threadfence();
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) *(volatile int*)(next_step + inst) = next;
+    }
+};
+
 template <class M, class T>
 __global__ void __launch_bounds__(32 * LaunchShape<M, T>::MAX_WARPS, 1)
 k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, int* queue, int tmem_cols) {
@@ -251,7 +278,110 @@ k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, co
     const WarpGroup<32> g;
     const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
     Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
-    for (int inst = next_instance(queue, o.order, gs.B); inst < gs.B; inst = next_instance(queue, o.order, gs.B)) closed_loop_step<M, T>(sv, inst, gs, a);
+    if (a.n_steps <= 1) {
+        for (int inst = next_instance(queue, o.order, gs.B); inst < gs.B; inst = next_instance(queue, o.order, gs.B)) closed_loop_step<M, T>(sv, inst, gs, a);
+    } else {      // tickets = (instance, chunk of control steps), issued instance-round-robin
+        DevTickets wq{queue, a.next_step};
+        const int total = gs.B * ((a.n_steps + a.chunk - 1) / a.chunk);
+        for (int t = wq.take(); t < total; t = wq.take()) closed_loop_chunk<M, T>(sv, t, gs, a, wq);
+    }
+    tmem_free_cta(tbase, tmem_cols);
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// slotted lockstep kernel (bnmpc_lockstep.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+// one lane of the sweep warp: it serves block `b` of the instance of warp slot `slot`
+struct SweepLane {
+    static constexpr int L = 1;
+    int lane;
+    __device__ __forceinline__ SweepLane() : lane(0) {}
+    template <class T> __device__ __forceinline__ T max(T v) const { return v; }
+    template <class T> __device__ __forceinline__ T sum(T v) const { return v; }
+    __device__ __forceinline__ bool any(bool p) const { return p; }
+    __device__ __forceinline__ bool all(bool p) const { return p; }
+    __device__ __forceinline__ void sync() const {}
+};
+
+struct LsShared {
+    int wstate[BNMPC_MAX_WARPS];          // LsWarp::published() of every warp, refreshed before the first barrier of a half-round
+    double par[BNMPC_MAX_WARPS][2];       // model parameters of every warp's instance, for the lanes of the sweep warp
+};
+
+// KIND 0: factorisation, 1: backward scan, 2: forward scan - for all instances of `mask` (bit = warp slot) at once, NBLK
+// lanes per instance, executed by one warp.  The lane's view of "its" instance is a Solver bound to that warp's working set.
+template <class M, class T, int KIND>
+__device__ __forceinline__ void ls_sweep(const Opts& o, const LsShared& sh, unsigned mask, int ws_of_slot) {
+    constexpr int NBLK = M::NBLK;
+    const int lane = (int)(threadIdx.x & 31), slot = lane / NBLK, b = lane % NBLK;
+    if (!((mask >> slot) & 1u) || slot >= BNMPC_MAX_WARPS) return;
+    const SweepLane gl;
+    const TmemPriv<M, T> ps{0u};
+    Solver<M, T, SweepLane, TmemPriv<M, T>> svs(nullptr, o.smem_stride * slot, o, gl, ps);
+    T p[M::NP];
+#pragma unroll
+    for (int j = 0; j < M::NP; j++) p[j] = T(sh.par[slot][j]);
+    svs.set_par(p);
+    svs.bind_block(b);
+    if (KIND == 0) svs.kkt_factor_blk(b);
+    else if (KIND == 1) svs.back_scan_blk(b);
+    else svs.fwd_scan_blk(b, (ws_of_slot & 7) - 1);
+}
+
+template <class M, class T>
+__global__ void __launch_bounds__(32 * LaunchShape<M, T>::MAX_WARPS, 1)
+k_loop_ls(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a, int* queue, int tmem_cols) {
+    __shared__ LsShared sh;
+    const uint32_t tbase = tmem_alloc_cta(tmem_cols);
+    const WarpGroup<32> g;
+    const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
+    using SV = Solver<M, T, WarpGroup<32>, TmemPriv<M, T>>;
+    SV sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
+    LsWarp<M, T, WarpGroup<32>, TmemPriv<M, T>> w;
+    w.reset();
+    DevTickets wq{queue, a.next_step};
+    const int W = (int)(blockDim.x >> 5), warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
+    static_assert(LaunchShape<M, T>::MAX_WARPS * M::NBLK <= 32, "the sweeps of a CTA must fit one warp");
+    const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+    int nprof = 1;
+    auto mark = [&](int tag, unsigned m0, unsigned m1) {
+        if (prof && nprof + 2 <= a.prof_cap) { a.prof[nprof++] = clock64(); a.prof[nprof++] = ((long long)tag << 56) | ((long long)m0 << 24) | (long long)(m1 & 0xffffffu); }
+    };
+    unsigned ipm_prev = 0;
+    for (;;) {
+        const int inst_before = w.inst;
+        mark(0, 0, 0);
+        ls_pslot<M, T>(1, w, sv, gs, a, wq, (ipm_prev & ~(1u << warp)) != 0);
+        if (w.inst != inst_before && w.inst >= 0 && lane < M::NP) sh.par[warp][lane] = double(sv.par[lane]);
+        if (lane == 0) sh.wstate[warp] = w.published();
+        mark(1, 0, 0);
+        __syncthreads();
+        const int ws = lane < W ? sh.wstate[lane] : 0;
+        const unsigned alive_m = __ballot_sync(0xffffffffu, (ws & LS_ALIVE) != 0);
+        const unsigned fac_m = __ballot_sync(0xffffffffu, (ws & 7) == 1), ipm_m = __ballot_sync(0xffffffffu, (ws & 7) != 0);
+        if (!alive_m) break;
+        ipm_prev = ipm_m;
+        const bool others = (ipm_m & ~(1u << warp)) != 0;
+        const int ws_slot = __shfl_sync(0xffffffffu, ws, lane / M::NBLK);       // state of the warp slot this lane would sweep for
+        mark(2, fac_m, ipm_m);
+        if (fac_m) { if (warp == 0) ls_sweep<M, T, 0>(o, sh, fac_m, ws_slot); mark(3, 0, 0); __syncthreads(); }
+        mark(4, 0, 0);
+        ls_pslot<M, T>(2, w, sv, gs, a, wq, others);
+        mark(5, 0, 0);
+        __syncthreads();
+        mark(6, 0, 0);
+        if (ipm_m) { if (warp == 0) ls_sweep<M, T, 1>(o, sh, ipm_m, ws_slot); mark(7, 0, 0); __syncthreads(); }
+        mark(8, 0, 0);
+        ls_pslot<M, T>(3, w, sv, gs, a, wq, others);
+        mark(9, 0, 0);
+        __syncthreads();
+        mark(10, 0, 0);
+        if (ipm_m) { if (warp == 0) ls_sweep<M, T, 2>(o, sh, ipm_m, ws_slot); mark(11, 0, 0); __syncthreads(); }
+        mark(12, 0, 0);
+        ls_pslot<M, T>(4, w, sv, gs, a, wq, others);
+    }
+    if (prof) a.prof[0] = nprof;
     tmem_free_cta(tbase, tmem_cols);
 }
 
@@ -276,6 +406,8 @@ struct OpsImpl {
     // (the opt-in maximum of a block minus the static part) and by tensor memory (512 columns, one column group per warp quad).
     static cudaError_t cta_shape(int N, int* warps) {
         cudaError_t e = prep(k_loop_step<M, T>, 0);
+        if (e != cudaSuccess) return e;
+        e = prep(k_loop_ls<M, T>, 0);
         if (e != cudaSuccess) return e;
         e = prep(k_solve<M, T>, 0);
         if (e != cudaSuccess) return e;
@@ -303,9 +435,15 @@ struct OpsImpl {
         k_loop_step<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N, warps));
         return cudaGetLastError();
     }
+    static cudaError_t loop_ls(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int* queue, cudaStream_t st) {
+        Opts o = o_;
+        o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
+        k_loop_ls<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N, warps));
+        return cudaGetLastError();
+    }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &cta_shape};
+                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &loop_ls, &cta_shape};
     }
 };
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BNMPC_VERSION 100
+#define BNMPC_VERSION 200
 
 /* models (reference src/force_model/dynamics.py:12-47, src/jerk_model/dynamics.py:12-52).  FORCE_DENSE solves the
  * force-model OCP without exploiting the x/z block structure (the generic coupled path; in-product cross-check). */
@@ -79,7 +79,8 @@ typedef struct bnmpc_config {
     int32_t sqp_max_iter;   /* acados nlp_solver_max_iter default 100 (nlp_solver_type SQP, src/force_model/ocp.py:86) */
     int32_t qp_max_iter;    /* acados qp_solver_iter_max default 50 */
     int32_t rti;            /* 1: one QP per solve, no NLP residual test (SQP_RTI of the north-star) */
-    int32_t threads_per_block; /* reserved (ignored): the launch shape is fixed, persistent CTAs of 4 warps */
+    int32_t threads_per_block; /* reserved (ignored): the launch shape follows from the model and the horizon - one persistent
+                               CTA per SM with as many warps (= instances in flight) as the on-chip memories hold */
     double dt;              /* interval length, tf / N (src/params.py:116, src/force_model/ocp.py:93) */
     double W[12];           /* diag of cost.W, order [x; u] (src/force_model/ocp.py:38-47) */
     double W_e[8];          /* diag of cost.W_e */
@@ -152,7 +153,10 @@ typedef struct bnmpc_closed_loop_args {
                                ref is [batch][4] = (radius, centre_x, centre_z, phase) of gen_circle_traj and every row
                                is computed on the fly with n = ref_rows - horizon samples per revolution (T = 10 s) */
     int32_t log_stride;     /* number of steps the log arrays were allocated for (>= first_step + n_steps) */
-    int32_t reserved;
+    int32_t steps_per_launch; /* <= 1: one kernel launch per control step (the latency path: step i is complete when launch i
+                               is).  k > 1: up to k control steps of every instance per launch - an instance keeps its working
+                               set on chip for a chunk of consecutive steps and instances advance independently of each
+                               other inside the launch (the Monte-Carlo throughput path; results are identical) */
     const double* ref;      /* gen_circle_traj layout, 8 columns [px pz vx vz ax az+g 0 0] (src/generate_trajectory.py:7-28) */
     const double* noise;    /* [log_stride][batch] or NULL: eps of step s for instance i (src/force_model/ocp.py:114) */
     /* optional logs (NULL to skip), [log_stride(+1)][dim][batch] */
@@ -162,6 +166,16 @@ typedef struct bnmpc_closed_loop_args {
     double* a_log;          /* [log_stride][2][batch]  force: u0/m (controller.py:38), jerk: a_i (jerk controller.py:45) */
     int32_t* status;        /* [log_stride][batch] */
     int32_t* qp_iter;       /* [log_stride][batch] */
+    /* Plant noise drawn on the device instead of read from `noise` (which must then be NULL): eps of (instance i, step s) =
+     * noise_std * N(0,1) from Philox4x32-10 with key = noise_seed and counter = (first_instance + i, s), Box-Muller on the
+     * first two 53-bit uniforms - one scalar per instance and step like np.random.normal(0, noise) at
+     * src/force_model/ocp.py:114-115, independent of batch size, sharding and launch shape (bnmpc_philox_noise gives the
+     * same numbers as an array). */
+    int32_t noise_philox;   /* 0 = off */
+    int32_t reserved;
+    uint64_t noise_seed;
+    double noise_std;       /* params.py:122 noise = 0.01 */
+    int64_t first_instance; /* global id of instance 0 of this handle (its rank's offset into the sharded batch) */
 } bnmpc_closed_loop_args;
 
 /* start of follow_trajectory: Xsim[0] = x0, a_i = [0, g], closedLoopCost = 0, zero iterate.
@@ -176,6 +190,13 @@ int bnmpc_gen_circle_table(void* handle, const double* params, int rows, double*
  * coordinates = calc_aed numerator, src/store_results.py:233-236), x [4][batch] current plant state, acc [2][batch]
  * (jerk a_i).  Any pointer may be NULL.  Device pointers. */
 int bnmpc_closed_loop_state(void* handle, double* cost, double* abs_err, double* x, double* acc);
+/* int32 [batch]: control steps since bnmpc_closed_loop_init whose solve returned a non-zero status.  The reference raises
+ * on the first one (src/force_model/controller.py:33-36); the fused loop keeps stepping - it applies u0 of the iterate the
+ * solver left, logs the status of the step - and counts, so that a run without per-step logs still reports failures. */
+int bnmpc_closed_loop_failures(void* handle, int32_t* out, int on_device);
+/* The draws of noise_philox as an array: out [n_steps][batch] (device pointer) = noise_std * N(0,1) of instances
+ * first_instance .. first_instance + batch - 1 at steps first_step .. first_step + n_steps - 1. */
+int bnmpc_philox_noise(void* handle, uint64_t seed, double noise_std, int64_t first_instance, int first_step, int n_steps, double* out);
 
 /* Measured FMA throughput of `device` in TFLOP/s for BNMPC_FP64 / BNMPC_FP32 (saturating kernel, 8 independent chains
  * per thread, best of 5): the denominator of the roofline fraction bench.py reports (MEASURED_PEAKS.json has no
@@ -189,6 +210,9 @@ int bnmpc_measure_fma_peak(int device, int precision, double* tflops);
  * acados divides on the CPU. */
 int bnmpc_selftest_rcp(int device, int64_t count, int solver_range, int64_t* mismatches);
 
+/* Debug aid (no reference counterpart): while buf != NULL, CTA 0 of every lockstep launch (steps_per_launch > 1) records
+ * (clock64, tag << 56 | masks) pairs at the barriers of its schedule into the device buffer buf[1..cap), buf[0] = words used. */
+int bnmpc_debug_profile(void* handle, long long* buf, int cap);
 /* number of kernels this library has launched on the handle since creation */
 int64_t bnmpc_launch_count(void* handle);
 const char* bnmpc_last_error(void);

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, '_build', 'libhostsim.so')
 _SRC = [os.path.join(_HERE, 'hostsim.cpp')] + [
     os.path.join(_HERE, '..', '..', 'drone_attitude_control_b200', 'csrc', f)
-    for f in ('bnmpc_core.cuh', 'bnmpc_loop.cuh', 'generated/models_gen.cuh')]
+    for f in ('bnmpc_core.cuh', 'bnmpc_loop.cuh', 'bnmpc_lockstep.cuh', 'generated/models_gen.cuh')]
 
 MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_JERK_DENSE, MODEL_THRUST = 0, 1, 2, 3, 4
 FP64, FP32 = 0, 1
@@ -89,7 +89,26 @@ def circle_table(params, rows, n):
     return out
 
 
-def closed_loop(model, prec, o, ref, x0, noise, p_ctrl, p_plant, n_steps, instance_major=False, circle_rows=None):
+def closed_loop(model, prec, o, ref, x0, noise, p_ctrl, p_plant, n_steps, instance_major=False, circle_rows=None, lockstep=None,
+                philox=None):
+    """lockstep = (chunk, W): run through the slotted lockstep schedule (bnmpc_lockstep.cuh) with one emulated CTA of W warps
+    and queue tickets of `chunk` control steps; philox = (seed, std, first_instance): noise drawn by the device-side generator."""
+    return _closed_loop(model, prec, o, ref, x0, noise, p_ctrl, p_plant, n_steps, instance_major, circle_rows, lockstep, philox)
+
+
+def philox_noise(B, n_steps, seed, std, first_instance=0, first_step=0):
+    out = np.zeros((n_steps, B))
+    lib().hs_philox_noise(B, n_steps, first_step, C.c_ulonglong(seed), C.c_double(std), C.c_longlong(first_instance), _dp(out))
+    return out
+
+
+def philox4x32(ctr, key):
+    c = (C.c_uint * 4)(*ctr); k = (C.c_uint * 2)(*key); o = (C.c_uint * 4)()
+    lib().hs_philox4x32(c, k, o)
+    return list(o)
+
+
+def _closed_loop(model, prec, o, ref, x0, noise, p_ctrl, p_plant, n_steps, instance_major, circle_rows, lockstep, philox):
     """ref [rows,8] shared or [B,rows,8]; x0 [B,4]; noise [n_steps,B]; p_* [B,2] (AoS like the oracle); converted to the
     layouts of the C-ABI (per-instance ref tables batch-minor [rows,8,B], or left instance-major).  Returns oracle-shaped
     arrays."""
@@ -105,8 +124,17 @@ def closed_loop(model, prec, o, ref, x0, noise, p_ctrl, p_plant, n_steps, instan
     pc = np.ascontiguousarray(p_ctrl.T, float); pp = np.ascontiguousarray(p_plant.T, float)
     Xsim = np.zeros((n_steps + 1, 4, B)); Up = np.zeros((n_steps, 2, B)); Uc = np.zeros((n_steps, 2, B)); al = np.zeros((n_steps, 2, B))
     cost = np.zeros(B); ae = np.zeros(B); st = np.zeros((n_steps, B), np.int32); qi = np.zeros((n_steps, B), np.int32)
-    rc = lib().hs_closed_loop(model, prec, C.byref(o), B, n_steps, rows, _dp(refd), int(shared), _dp(x0t), _dp(nz), _dp(pc), _dp(pp),
-                              _dp(Xsim), _dp(Up), _dp(Uc), _dp(al), _dp(cost), _dp(ae), _ip(st), _ip(qi))
+    fails = np.zeros(B, np.int32)
+    if lockstep is None:
+        assert philox is None
+        rc = lib().hs_closed_loop(model, prec, C.byref(o), B, n_steps, rows, _dp(refd), int(shared), _dp(x0t), _dp(nz), _dp(pc), _dp(pp),
+                                  _dp(Xsim), _dp(Up), _dp(Uc), _dp(al), _dp(cost), _dp(ae), _ip(st), _ip(qi))
+    else:
+        chunk, W = lockstep
+        seed, std, i0 = philox if philox is not None else (0, 0.0, 0)
+        rc = lib().hs_closed_loop_ls(model, prec, C.byref(o), B, n_steps, int(chunk), int(W), rows, _dp(refd), int(shared), _dp(x0t),
+                                     _dp(nz), _dp(pc), _dp(pp), _dp(Xsim), _dp(Up), _dp(Uc), _dp(al), _dp(cost), _dp(ae), _ip(st),
+                                     _ip(qi), _ip(fails), C.c_ulonglong(seed), C.c_double(std), C.c_longlong(i0))
     assert rc == 0, rc
-    return dict(cost=cost, abs_err=ae, Xsim=np.transpose(Xsim, (2, 0, 1)), U_plant=np.transpose(Up, (2, 0, 1)),
+    return dict(failures=fails, cost=cost, abs_err=ae, Xsim=np.transpose(Xsim, (2, 0, 1)), U_plant=np.transpose(Up, (2, 0, 1)),
                 U_ctrl=np.transpose(Uc, (2, 0, 1)), a=np.transpose(al, (2, 0, 1)), status=st.T.copy(), qp_iter=qi.T.copy())

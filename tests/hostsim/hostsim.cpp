@@ -11,7 +11,7 @@
 #include <stdlib.h>
 #include <vector>
 
-#include "../../drone_attitude_control_b200/csrc/bnmpc_loop.cuh"
+#include "../../drone_attitude_control_b200/csrc/bnmpc_lockstep.cuh"
 
 using namespace bnmpc;
 
@@ -108,6 +108,76 @@ static int closed_loop_t(const Opts* o, int kind, int B, int n_steps, int rows, 
     return 0;
 }
 
+// The slotted lockstep schedule of bnmpc_lockstep.cuh with one emulated CTA of W "warps": the pass slots run warp after
+// warp (the CTA barriers of the kernel are implicit), the sweep slots call the instance's own sweep functions.  Checks the
+// state machine (ls_pslot), the ticket / chunk hand-over and the multi-step residency against the per-step path.
+struct HostTickets {
+    int next = 0; std::vector<int>* ns;
+    int take() { return next++; }
+    bool ready(int inst, int step) const { return (*ns)[inst] == step; }
+    void wait(int inst, int step) const { if (!ready(inst, step)) abort(); }    // tickets run in order here: never blocks
+    void publish(int inst, int nx) { (*ns)[inst] = nx; }
+};
+
+template <class M, class T>
+static int closed_loop_ls_t(const Opts* o, int kind, int B, int n_steps, int chunk, int W, int rows, const double* ref, int ref_shared,
+                            const double* x0, const double* noise, const double* p_ctrl, const double* p_plant, double* Xsim,
+                            double* U_plant, double* U_ctrl, double* a_log, double* cost, double* abs_err, int* status, int* qp_iter,
+                            int* fail_count, unsigned long long philox_seed, double philox_std, long long inst0) {
+    const int N = o->N;
+    if (rows < n_steps + N) return -1;
+    using SV = Solver<M, T, HostGroup, SmemPriv<M, T>>;
+    Sim<M, T> sim(B, N);
+    HostGroup g;
+    const size_t Bp = B;
+    std::vector<double> xs(4 * Bp), acc(2 * Bp), pp(2 * Bp);
+    std::vector<int> next_step(B, 0);
+    for (int i = 0; i < B; i++) {
+        for (int j = 0; j < 4; j++) { xs[j * Bp + i] = x0[j * B + i]; if (Xsim) Xsim[(size_t)j * B + i] = x0[j * B + i]; }
+        acc[i] = 0.0; acc[Bp + i] = p_ctrl[B + i];
+        pp[i] = p_plant[i]; pp[Bp + i] = p_plant[B + i];
+        cost[i] = 0; abs_err[i] = 0; if (fail_count) fail_count[i] = 0;
+        const double pc[2] = {p_ctrl[i], p_ctrl[B + i]};
+        sim.set(i, F_P, 0, pc);
+    }
+    LoopArgs a{};
+    a.step = 0; a.n_steps = n_steps; a.chunk = chunk; a.kind = kind; a.ref_layout = ref_shared; a.ref_rows = rows; a.log_stride = n_steps;
+    a.batch = B; a.Bp = Bp; a.ref = ref; a.noise = noise; a.Xsim = Xsim; a.U_plant = U_plant; a.U_ctrl = U_ctrl; a.a_log = a_log;
+    a.status = status; a.qp_iter = qp_iter; a.xs = xs.data(); a.acc = acc.data(); a.cost = cost; a.abs_err = abs_err; a.p_plant = pp.data();
+    a.fail_count = fail_count; a.next_step = next_step.data();
+    if (philox_std > 0) { a.noise = nullptr; a.noise_philox = 1; a.noise_seed = philox_seed; a.noise_std = philox_std; a.inst0 = inst0; }
+    const SmemPriv<M, T> ps;
+    if (W == 0) {      // the free-running multi-step path of k_loop_step: one group, tickets in order
+        std::vector<T> sm1(SmLayout<M, true>::elems(N), T(0));
+        SV sv1(sm1.data(), 0, *o, g, ps);
+        HostTickets wq1; wq1.ns = &next_step;
+        const int total = B * ((n_steps + chunk - 1) / chunk);
+        for (int t = wq1.take(); t < total; t = wq1.take()) closed_loop_chunk<M, T>(sv1, t, sim.gs, a, wq1);
+        return 0;
+    }
+    std::vector<std::vector<T>> sm(W, std::vector<T>(SmLayout<M, true>::elems(N), T(0)));
+    std::vector<SV> sv; sv.reserve(W);
+    std::vector<LsWarp<M, T, HostGroup, SmemPriv<M, T>>> w(W);
+    for (int i = 0; i < W; i++) { sv.emplace_back(sm[i].data(), 0, *o, g, ps); w[i].reset(); }
+    HostTickets wq; wq.ns = &next_step;
+    std::vector<int> ws(W);
+    for (long half = 0;; half++) {
+        if (half > 400L * n_steps * ((B + W - 1) / W) + 1000) return -3;      // the schedule must terminate
+        for (int i = 0; i < W; i++) ls_pslot<M, T>(1, w[i], sv[i], sim.gs, a, wq);
+        bool alive = false;
+        for (int i = 0; i < W; i++) { ws[i] = w[i].published(); alive = alive || (ws[i] & LS_ALIVE); }
+        if (!alive) break;
+        for (int i = 0; i < W; i++) if ((ws[i] & 7) == 1) sv[i].kkt_factor();
+        for (int i = 0; i < W; i++) ls_pslot<M, T>(2, w[i], sv[i], sim.gs, a, wq);
+        for (int i = 0; i < W; i++) if ((ws[i] & 7) != 0) sv[i].back_scan();
+        for (int i = 0; i < W; i++) ls_pslot<M, T>(3, w[i], sv[i], sim.gs, a, wq);
+        for (int i = 0; i < W; i++) if ((ws[i] & 7) != 0) sv[i].fwd_scan((ws[i] & 7) - 1);
+        for (int i = 0; i < W; i++) ls_pslot<M, T>(4, w[i], sv[i], sim.gs, a, wq);
+    }
+    for (int i = 0; i < B; i++) if (next_step[i] != n_steps) return -4;
+    return 0;
+}
+
 #define DISPATCH(fn, model, prec, ...)                                                     \
     switch ((model) * 2 + (prec)) {                                                        \
     case 0: return fn<Model_force, double>(__VA_ARGS__);                                   \
@@ -143,4 +213,19 @@ int hs_closed_loop(int model, int prec, const Opts* o, int B, int n_steps, int r
     DISPATCH(closed_loop_t, model, prec, o, kind, B, n_steps, rows, ref, ref_shared, x0, noise, p_ctrl, p_plant, Xsim, U_plant, U_ctrl,
              a_log, cost, abs_err, status, qp_iter)
 }
+// the same closed loop through the slotted lockstep schedule (one emulated CTA of W warps, tickets of `chunk` steps);
+// philox_std > 0: the noise is drawn by philox_normal(seed, inst0 + i, step) instead of read from `noise`
+int hs_closed_loop_ls(int model, int prec, const Opts* o, int B, int n_steps, int chunk, int W, int rows, const double* ref, int ref_shared,
+                      const double* x0, const double* noise, const double* p_ctrl, const double* p_plant, double* Xsim, double* U_plant,
+                      double* U_ctrl, double* a_log, double* cost, double* abs_err, int* status, int* qp_iter, int* fail_count,
+                      unsigned long long philox_seed, double philox_std, long long inst0) {
+    const int kind = (model == 1 || model == 3) ? KIND_JERK : (model == 4 ? KIND_THRUST : KIND_FORCE);
+    DISPATCH(closed_loop_ls_t, model, prec, o, kind, B, n_steps, chunk, W, rows, ref, ref_shared, x0, noise, p_ctrl, p_plant, Xsim, U_plant,
+             U_ctrl, a_log, cost, abs_err, status, qp_iter, fail_count, philox_seed, philox_std, inst0)
+}
+// noise_std * N(0,1) of the device-side generator, [n_steps][B]
+void hs_philox_noise(int B, int n_steps, int first_step, unsigned long long seed, double std_, long long inst0, double* out) {
+    for (int s = 0; s < n_steps; s++) for (int i = 0; i < B; i++) out[(size_t)s * B + i] = std_ * philox_normal(seed, inst0 + i, first_step + s);
+}
+void hs_philox4x32(const unsigned* ctr, const unsigned* key, unsigned* out) { philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out); }
 }

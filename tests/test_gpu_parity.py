@@ -26,15 +26,16 @@ def _gold_err(series, g, name):
     return float(np.max(np.abs(series[st[m]] - v[m])))
 
 
-def _run_loop(model, refs, x0, noise, pc, pp, S, layout='instance_major', **kw):
+def _run_loop(model, refs, x0, noise, pc, pp, S, layout='instance_major', steps_per_launch=1, **kw):
     """refs [rows, 8] (shared table) or [B, rows, 8]; the latter is passed instance-major or batch-minor ([rows, 8, B])"""
     loop = pkg.BatchedClosedLoop(model, batch=x0.shape[0], device=0, **kw)
     if refs.ndim == 2 or layout == 'instance_major':
         ref_t = torch.tensor(np.ascontiguousarray(refs))
     else:
         ref_t = torch.tensor(np.ascontiguousarray(np.transpose(refs, (1, 2, 0))))
-    loop.init(torch.tensor(x0.T.copy()), ref_t, noise=None if noise is None else torch.tensor(noise),
-              p_ctrl=torch.tensor(pc.T.copy()), p_plant=torch.tensor(pp.T.copy()), n_steps=S).run()
+    nz = noise if isinstance(noise, pkg.PhiloxNoise) else (None if noise is None else torch.tensor(noise))
+    loop.init(torch.tensor(x0.T.copy()), ref_t, noise=nz,
+              p_ctrl=torch.tensor(pc.T.copy()), p_plant=torch.tensor(pp.T.copy()), n_steps=S).run(steps_per_launch=steps_per_launch)
     r = {k: v.cpu().numpy() for k, v in loop.results().items()}
     return r, loop
 
@@ -493,6 +494,55 @@ def test_results_do_not_depend_on_the_launch_shape(monkeypatch):
             assert np.array_equal(got[k], base[k]), (env, k)
         for k in env:
             monkeypatch.delenv(k)
+
+
+@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense'])
+def test_lockstep_and_multi_step_launches_are_bit_identical(model, monkeypatch):
+    """Three schedules of the same closed loop - one warp per instance with a work queue (k_loop_step), the slotted lockstep
+    kernel one launch per step, and the lockstep kernel with many steps per launch (working set resident for a chunk of steps,
+    tickets handed between SMs) - only move work in time: every output is bit-identical, and equal to the oracle's."""
+    B, S = 700, 14
+    refs, x0, noise, pc, pp = _fast_loop_inputs(B, S, seed=15, mass_sigma=0.05)
+    monkeypatch.setenv('BNMPC_LOOP_KERNEL', 'warp')
+    base, _ = _run_loop(model, refs, x0, noise, pc, pp, S)
+    monkeypatch.setenv('BNMPC_LOOP_KERNEL', 'ls')
+    keys = ('Xsim', 'U_ctrl', 'U_plant', 'a', 'cost', 'aed', 'status', 'qp_iter', 'failures')
+    for env, spl in (({}, 1), ({}, S), ({'BNMPC_CHUNK': '3'}, S), ({'BNMPC_CHUNK': '1', 'BNMPC_WARPS_PER_SM': '3'}, 5),
+                     ({'BNMPC_CHUNK': '4', 'BNMPC_NO_ORDER': '1'}, 9)):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got, _ = _run_loop(model, refs, x0, noise, pc, pp, S, steps_per_launch=spl)
+        for k in keys:
+            assert np.array_equal(got[k], base[k]), (env, spl, k)
+        for k in env:
+            monkeypatch.delenv(k)
+    om = MODEL_ID[model]
+    sub = np.arange(0, B, 29)
+    want = co.closed_loop(co.default_opts(om), refs[sub], x0[sub], noise[:, sub], pc[sub], pp[sub], S)
+    assert np.array_equal(base['status'][sub], want['status']) and np.array_equal(base['qp_iter'][sub], want['qp_iter'])
+    np.testing.assert_allclose(base['Xsim'][sub], want['Xsim'], rtol=0, atol=1e-9)
+
+
+def test_philox_noise_on_device_matches_the_array_path():
+    """PhiloxNoise: the scalar np.random.normal(0, noise) of simulate_next_x (src/force_model/ocp.py:114-115) drawn in the
+    kernel from (seed, global instance, step).  Same numbers as bnmpc_philox_noise materialises, as the host mirror of the
+    generator computes (up to libm rounding of log / cos), independent of the sharding, and the loop that draws them in the
+    kernel equals the loop fed with the array bit for bit."""
+    import hostsim as hs
+    B, S = 300, 12
+    refs, x0, _, pc, pp = _fast_loop_inputs(B, S, seed=3)
+    ph = pkg.PhiloxNoise(seed=77, std=0.01, first_instance=1000)
+    got, loop = _run_loop('force', refs, x0, ph, pc, pp, S, steps_per_launch=S)
+    arr = loop.noise_array().cpu().numpy()
+    np.testing.assert_allclose(arr, hs.philox_noise(B, S, 77, 0.01, first_instance=1000), rtol=0, atol=1e-16)
+    assert abs(arr.std() - 0.01) < 5e-4
+    want, _ = _run_loop('force', refs, x0, arr, pc, pp, S)
+    for k in ('Xsim', 'U_ctrl', 'cost', 'status', 'qp_iter'):
+        assert np.array_equal(got[k], want[k]), k
+    half = B // 2           # second half of the batch as its own "rank": same draws
+    ph2 = pkg.PhiloxNoise(seed=77, std=0.01, first_instance=1000 + half)
+    part, _ = _run_loop('force', refs[half:], x0[half:], ph2, pc[half:], pp[half:], S, steps_per_launch=4)
+    assert np.array_equal(part['Xsim'], got['Xsim'][half:])
 
 
 def test_work_queue_ring_wraps():

@@ -78,3 +78,77 @@ def test_nonlinear_thrust_ocp_matches_oracle():
     assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
     for k in ('Xsim', 'U_ctrl', 'U_plant', 'a'):
         np.testing.assert_allclose(got[k], want[k], rtol=0, atol=1e-10, err_msg=k)
+
+
+@pytest.mark.parametrize('model,chunk,W', [(0, 1, 3), (0, 4, 5), (1, 25, 2), (0, 7, 16), (hs.MODEL_THRUST, 3, 4), (0, 6, 0), (1, 1, 0), (hs.MODEL_THRUST, 5, 0)])
+def test_lockstep_schedule_is_bit_identical(model, chunk, W):
+    """Multi-step launches - queue tickets of `chunk` control steps with the working set kept on chip inside a chunk, run by
+    free warps (W = 0: closed_loop_chunk, the path of k_loop_step) or by the slotted lockstep schedule (bnmpc_lockstep.cuh: W
+    warps of a CTA side by side, sweeps in sweep slots) - only re-time the work of an instance: every output must equal the
+    one-launch-per-step path bit for bit, for any number of warps and any chunk length."""
+    from common import thrust_refs
+    S, B = 25, 7
+    om = co.MODEL_THRUST if model == hs.MODEL_THRUST else model
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=13 + model, mass_sigma=0.05)
+    if model == hs.MODEL_THRUST:
+        refs, S = thrust_refs(refs), 8
+        noise = noise[:S]
+    oo = hs.opts_from_oracle(co.default_opts(om))
+    a = hs.closed_loop(model, hs.FP64, oo, refs, x0, noise, pc, pp, S, instance_major=True)
+    b = hs.closed_loop(model, hs.FP64, oo, refs, x0, noise, pc, pp, S, instance_major=True, lockstep=(chunk, W))
+    for k in ('Xsim', 'U_ctrl', 'U_plant', 'a', 'cost', 'abs_err', 'qp_iter', 'status'):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(b['failures'], (a['status'] != 0).sum(1))
+
+
+def test_lockstep_rti_and_failures():
+    """SQP_RTI through the lockstep schedule, and the failure path: a NaN in the reference gives status 1 for the steps
+    whose window sees it, the loop keeps going, the instance's failure count says how often, and the solver state an
+    instance carries across a failed step is what the per-step path carries (multipliers of the last good solve)."""
+    S, B = 12, 4
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=31)
+    oo = co.default_opts(0, rti=True)
+    want = co.closed_loop(oo, refs, x0, noise, pc, pp, S)
+    got = hs.closed_loop(0, hs.FP64, hs.opts_from_oracle(oo), refs, x0, noise, pc, pp, S, instance_major=True, lockstep=(5, 3))
+    assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
+    np.testing.assert_allclose(got['Xsim'], want['Xsim'], rtol=0, atol=1e-10)
+    refs = refs.copy()
+    refs[2, 30 + 3, 1] = np.nan                    # enters the window of instance 2 at step 3 (terminal stage) and stays until step 33
+    oo = hs.opts_from_oracle(co.default_opts(0))
+    a = hs.closed_loop(0, hs.FP64, oo, refs, x0, noise, pc, pp, S, instance_major=True)
+    b = hs.closed_loop(0, hs.FP64, oo, refs, x0, noise, pc, pp, S, instance_major=True, lockstep=(4, 3))
+    assert (a['status'][2, 3:] == 1).all() and (a['status'][2, :3] == 0).all() and (a['status'][[0, 1, 3]] == 0).all()
+    for k in ('U_ctrl', 'qp_iter', 'status'):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(np.nan_to_num(a['Xsim'], nan=-7.0), np.nan_to_num(b['Xsim'], nan=-7.0))
+    assert b['failures'].tolist() == [0, 0, S - 3, 0]
+    # QP failure (status 4): a start state far outside the position box makes the first QPs infeasible
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=32)
+    x0[1, 0] += 4.0
+    a = hs.closed_loop(0, hs.FP64, oo, refs, x0, noise, pc, pp, S, instance_major=True)
+    assert (a['status'][1] == 4).any() and (a['status'][[0, 2, 3]] == 0).all()
+    for sched in ((6, 3), (5, 0)):
+        b = hs.closed_loop(0, hs.FP64, oo, refs, x0, noise, pc, pp, S, instance_major=True, lockstep=sched)
+        for k in ('Xsim', 'U_ctrl', 'qp_iter', 'status', 'cost'):
+            assert np.array_equal(a[k], b[k]), (sched, k)
+        assert b['failures'][1] == (a['status'][1] != 0).sum()
+
+
+def test_philox_noise_generator():
+    """Known-answer test of Philox4x32-10 (Random123 kat_vectors: counter 0 / key 0 and the all-ones vector) and the
+    statistics / sharding-independence of the normal draws built on it."""
+    assert hs.philox4x32([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert hs.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    z = hs.philox_noise(4096, 50, seed=2026, std=1.0)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01 and np.abs(z).max() < 6.5
+    part = hs.philox_noise(100, 50, seed=2026, std=1.0, first_instance=1000)
+    assert np.array_equal(part, z[:, 1000:1100])
+    later = hs.philox_noise(4096, 10, seed=2026, std=1.0, first_step=40)
+    assert np.array_equal(later, z[40:])
+    S, B = 10, 5
+    refs, x0, _, pc, pp = random_loop_inputs(B, S, seed=2)
+    oo = hs.opts_from_oracle(co.default_opts(0))
+    nz = hs.philox_noise(B, S, seed=99, std=0.01, first_instance=12)
+    a = hs.closed_loop(0, hs.FP64, oo, refs, x0, nz, pc, pp, S, instance_major=True, lockstep=(3, 2))
+    b = hs.closed_loop(0, hs.FP64, oo, refs, x0, None, pc, pp, S, instance_major=True, lockstep=(3, 2), philox=(99, 0.01, 12))
+    assert np.array_equal(a['Xsim'], b['Xsim']) and np.array_equal(a['U_ctrl'], b['U_ctrl'])
