@@ -4,17 +4,27 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model force|jerk] [--batch B]
 
 A "step" is one control step for the whole batch of drones: yref windowing + x0 embedding + SQP/HPIPM solve + converter
-+ plant step + logs, ONE kernel launch (bnmpc_closed_loop_run).  Workload at every N: BASELINE config 2, "force_model
++ plant step + logs (bnmpc_closed_loop_run).  Workload of the headline at every N: BASELINE config 2, "force_model
 batched closed-loop, 4096 drones with randomised x0 and trajectories, FP64" per GPU (weak scaling: each rank owns its
-own 4096 instances, no data-path collective).  Inputs are resident in HBM for `value`; `e2e` is the same metric through
-the AcadosOcpSolver-style shim with pinned HOST buffers (yref window + x0 in, u0 + status out, every step).
+own 4096 instances, no data-path collective).
+
+  value   K control steps of every drone in ONE launch (steps_per_launch = K: queue tickets of (drone, chunk of steps),
+          the working set of a drone stays on chip inside a chunk - the Monte-Carlo throughput path), inputs resident in HBM
+  per_step_launch   the same K steps as K launches (every launch ends with all drones at the same step - the latency
+          path: p50 / p99 step latency), L2 flushed between launches
+  e2e     the reference's own loop shape through the AcadosOcpSolver / AcadosSimSolver-style shim with pinned HOST
+          buffers, every step: set_up_ocp (yref window), solve_for_x0 (x0 in, u0 + status out), Converter on the host,
+          simulate_next_x (x, u, noise in, x_next out)
+  extra   bounded runs of BASELINE configs 3 (jerk 16384, FP64 + FP32), 4 (262144 drones with plant-mass perturbation,
+          SHARDED over the N ranks - strong scaling) and 5 (horizon 20 / 50 / 100 at 65536 drones)
 
 --impl reference times the CPU restatement of the reference's path (oracle/nmpc_oracle.c, all host threads) - acados
-itself is not installable here - on the same workload, a bounded sample of instances per step.
+itself is not installable here - on the same instances (same generator, same global ids), a bounded sample.
 """
 import argparse
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -26,25 +36,42 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'nmpc_solves_per_sec'
 UNIT = 'solves/s'
+SEED = 2026
+MODEL_DIMS = dict(force=(2, 2, 1, 4, 2, 4), jerk=(2, 3, 1, 6, 2, 1), force_dense=(1, 4, 2, 4, 2, 4), thrust=(1, 4, 2, 4, 2, 4))   # nblk n m nx nu erk
 
 
-def flops_per_solve(nblk, n, m, N, erk_stages, qp_iters, sqp_iters=1.0):
+def flops_per_solve(nblk, n, m, N, erk_stages, qp_iters, linearisations=1.0):
     """Algorithmic flops (SURVEY 8d formulas, applied to the block structure the solver actually factorises):
     per stage factorisation s n^2 + s^2 n + s^3/3, one KKT solve 4n^2 + 4sn + 2s^2, residuals/barrier 2(2sn + s^2) + 10s;
-    per IPM iteration N (F_f + 2 F_s + F_r); linearisation N (S_rk 2 n^2 s + 2 s^2)."""
+    per IPM iteration N (F_f + 2 F_s + F_r); per linearisation N (S_rk 2 n^2 s + 2 s^2) - SQP to tolerance linearises once
+    more than it solves QPs (the residual test that ends it), SQP_RTI exactly once."""
     s = n + m
     f_f = s * n * n + s * s * n + s ** 3 / 3.0
     f_s = 4 * n * n + 4 * s * n + 2 * s * s
     f_r = 2 * (2 * s * n + s * s) + 10 * s
     f_it = nblk * N * (f_f + 2 * f_s + f_r)
     f_lin = nblk * N * (erk_stages * 2 * n * n * s + 2 * s * s)
-    return sqp_iters * f_lin + qp_iters * f_it
+    return linearisations * f_lin + qp_iters * f_it
 
 
 def bytes_per_solve(nx, nu, N):
     """Algorithmic HBM bytes of one closed-loop step: x0 + yref window in, u0 + status/iters out, plus the
     rollout's state r/w, noise and p."""
     return nx * 8 + (N * (nx + nu) + nx) * 8 + nu * 8 + 8 + 64 + 8 + 16
+
+
+def config_dict(args):
+    """What both arms print as `config` (identical for --impl ours and --impl reference)."""
+    return {'workload': f'{args.model}_model batched closed loop, {args.batch} drones per GPU with randomised x0 and circle trajectories '
+                        f'(BASELINE config 2), N_horizon {args.horizon}, {"SQP_RTI" if args.rti else "SQP to tol 1e-6"} + HPIPM-style IPM, '
+                        f'noise sigma 0.01',
+            'batch_per_gpu': args.batch, 'horizon': args.horizon, 'controller': args.model, 'precision': args.precision,
+            'plant_mass_sigma': args.mass_sigma,
+            'instances': f'sharding.instance_inputs(seed {SEED}): Philox draws keyed by the global instance id, per-instance circle tables',
+            'reference_table': 'per-instance table [B, rows, 8] in HBM' if args.ref == 'table' else 'generated in the kernel (CircleRef)',
+            'l2': 'GPU arm - value: one launch over per-instance tables larger than L2 (157 MB), L2 flushed before it; per_step_launch: '
+                  'flushed between launches (256 MiB write, untimed)',
+            'timing': 'GPU arm: CUDA events on the launch stream, max over ranks; CPU arm: perf_counter around the timed steps'}
 
 
 class ClockSampler:
@@ -71,7 +98,7 @@ class ClockSampler:
                 for bit, name in names.items():
                     if isinstance(bit, int) and bit and (r & bit) == bit and bit & (bit - 1) == 0:
                         self.reasons.add(name.replace('nvmlClocksEventReason', '').replace('nvmlClocksThrottleReason', ''))
-                time.sleep(0.05)
+                time.sleep(0.02)
         except Exception as e:   # noqa: BLE001
             self.reasons.add(f'sampler_error:{type(e).__name__}')
 
@@ -90,45 +117,93 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': self.max_mhz, 'reasons': rs, 'samples': len(self.samples)}
 
 
-def make_inputs(lo, hi, n_steps, rows, device, mass_sigma=0.0):
-    """BASELINE config 2 / 4 / SURVEY 8d inputs for the global instances lo..hi-1 (per-instance seeds keyed by the global
-    id: the numbers do not depend on how many ranks share the batch)."""
+def workload(lo, hi, n_steps, rows, N, mass_sigma=0.0, with_noise=True):
+    """BASELINE config 2 / 4 / SURVEY 8d inputs of the global instances lo..hi-1 as CPU tensors: the circle parameters, the
+    reference table ref [rows, 8, b], x0 [4, b], the noise [n_steps, b] and the plant mass scale - from the per-instance
+    Philox draws of sharding.instance_inputs, so the numbers do not depend on how many ranks share the batch and BOTH arms
+    of the bench (GPU and CPU reference) run exactly these instances."""
     from drone_attitude_control_b200.generate_trajectory import gen_circle_traj_batched
     from drone_attitude_control_b200.sharding import instance_inputs
-    inp = instance_inputs(lo, hi, n_steps, mass_sigma=mass_sigma)
-    ref = gen_circle_traj_batched(500, rows - 500, inp['radius'], inp['center'], inp['phase'], device=device)      # [rows, 8, b]
-    x0 = ref[0, :4, :].clone() + inp['dx0'].to(device)
-    return ref, x0, inp['noise'].to(device), inp
+    inp = instance_inputs(lo, hi, n_steps, seed=SEED, mass_sigma=mass_sigma, with_noise=with_noise)
+    n_rev = max(500, rows - N)
+    ref = gen_circle_traj_batched(n_rev, rows - n_rev, inp['radius'], inp['center'], inp['phase'])      # [rows, 8, b]
+    inp['ref'] = ref
+    inp['x0'] = ref[0, :4, :].clone() + inp['dx0']
+    return inp
+
+
+def native_oracle(model):
+    """The C restatement rebuilt for THIS host (bench.py runs on the GPU box): -O3 -march=native with the model's dimensions
+    as compile-time constants (ORC_FIXED_NX / NU), so the CPU baseline is the port at its best.  Timing only - the parity
+    tests use the generic build."""
+    from oracle import c_oracle as co
+    nx, nu = (6, 2) if model == 'jerk' else (4, 2)
+    src = os.path.join(ROOT, 'oracle', 'nmpc_oracle.c')
+    out = os.path.join(ROOT, 'oracle', '_build', f'libnmpc_oracle_native_{nx}_{nu}.so')
+    flags = ['-O3', '-march=native', f'-DORC_FIXED_NX={nx}', f'-DORC_FIXED_NU={nu}']
+    try:
+        if not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            os.makedirs(os.path.dirname(out), exist_ok=True)
+            subprocess.check_call(['gcc'] + flags + ['-pthread', '-fPIC', '-shared', '-o', out, src, '-lm'])
+        return co.load_variant(out), ' '.join(flags)
+    except Exception as e:   # noqa: BLE001
+        return co.lib(), f'generic build -O3 -mavx2 -mfma (native rebuild failed: {type(e).__name__})'
+
+
+def cpu_closed_loop(args, inp, n_inst, warm, steps):
+    """The oracle on the first n_inst instances of `inp`: returns (seconds for `steps` steps after `warm` warm-up steps,
+    qp_iter mean over the timed steps, nonzero statuses, cores, build flags)."""
+    from oracle import c_oracle as co
+    L, flags = native_oracle(args.model)
+    model = co.MODEL_JERK if args.model.startswith('jerk') else co.MODEL_FORCE
+    cores = co.lib().orc_num_cores()
+    refs = inp['ref'][:, :, :n_inst].permute(2, 0, 1).contiguous().numpy()
+    x0 = inp['x0'][:, :n_inst].numpy().T.copy()
+    noise = inp['noise'][:, :n_inst].contiguous().numpy()
+    pc = np.repeat(np.array([[0.03277, 9.81]]), n_inst, 0)
+    pp = pc.copy(); pp[:, 0] *= inp['mass_scale'][:n_inst].numpy()
+    opts = co.default_opts(model, N=args.horizon, rti=args.rti)
+    nw = min(cores, n_inst)
+    co.closed_loop(opts, refs[:nw], x0[:nw], np.ascontiguousarray(noise[:2, :nw]), pc[:nw], pp[:nw], 2, outputs=False, L=L)     # warm the threads
+    # the oracle API runs whole loops: time the (warm + steps)-step run and the warm-step run and subtract
+    t0 = time.perf_counter(); co.closed_loop(opts, refs, x0, noise, pc, pp, warm, nthreads=cores, outputs=False, L=L); tw = time.perf_counter() - t0
+    t0 = time.perf_counter(); out = co.closed_loop(opts, refs, x0, noise, pc, pp, warm + steps, nthreads=cores, outputs=True, L=L); tk = time.perf_counter() - t0
+    qp = out['qp_iter'][:, warm:warm + steps]
+    return max(tk - tw, 1e-9), float(qp.mean()), int((out['status'][:, warm:warm + steps] != 0).sum()), cores, flags
 
 
 def run_ours(args):
+    import ctypes as C
     import torch
     import torch.distributed as dist
     import drone_attitude_control_b200 as pkg
     from drone_attitude_control_b200 import _lib
-    import ctypes as C
+    from drone_attitude_control_b200.sharding import shard_range
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.gpus != world:
+        raise SystemExit(f'bench.py --gpus {args.gpus} but WORLD_SIZE is {world}: launch N > 1 as python -m torch.distributed.run '
+                         f'--nnodes=1 --nproc-per-node {args.gpus} --master-addr 127.0.0.1 bench.py --gpus {args.gpus} ...')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    B, K, W = args.batch, args.steps, args.warmup
-    N = args.horizon
-    rows = max(500 + N, W + K + N + 1)
-    ref, x0, noise, inp = make_inputs(rank * B, (rank + 1) * B, W + K, rows, device=dev, mass_sigma=args.mass_sigma)   # weak scaling
-    ref_im = ref.permute(2, 0, 1).contiguous()                                             # [B, rows, 8] instance-major
+    B, K, W, N = args.batch, args.steps, args.warmup, args.horizon
+    S = W + 2 * K                                   # warm-up, K steps in one launch, K steps as K launches
+    rows = max(500 + N, S + N + 1)
+    inp = workload(rank * B, (rank + 1) * B, S, rows, N, mass_sigma=args.mass_sigma)   # weak scaling: global ids rank*B ..
+    ref_im = inp['ref'].permute(2, 0, 1).contiguous().to(dev)                           # [B, rows, 8] instance-major
+    x0, noise = inp['x0'].to(dev), inp['noise'].to(dev)
     loop = pkg.BatchedClosedLoop(args.model, batch=B, device=local, precision=args.precision, N_horizon=N, rti=args.rti)
     p_plant = None
-    if args.mass_sigma > 0:                                                                # BASELINE config 4: model mismatch
-        import torch as _t
-        p_plant = _t.stack([0.03277 * inp['mass_scale'], _t.full((B,), 9.81, dtype=_t.float64)])
-    ref_arg = pkg.CircleRef(inp['radius'], inp['center'], inp['phase'], n=rows - N) if args.ref == 'circle' else ref_im
-    loop.init(x0, ref_arg, noise=noise, p_plant=p_plant, n_steps=W + K, log=True)
+    if args.mass_sigma > 0:                                                             # BASELINE config 4: model mismatch
+        p_plant = torch.stack([0.03277 * inp['mass_scale'], torch.full((B,), 9.81, dtype=torch.float64)])
+    ref_arg = pkg.CircleRef(inp['radius'], inp['center'], inp['phase'], n=max(500, rows - N)) if args.ref == 'circle' else ref_im
+    loop.init(x0, ref_arg, noise=noise, p_plant=p_plant, n_steps=S, log=True)
     stream = torch.cuda.current_stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_l2 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -136,101 +211,60 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    loop.run(W)                                   # warm-up steps (untimed)
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    loop.run(W)                                   # warm-up steps (untimed, one launch each)
+    flush.fill_(1)
     barrier()
+    # ---- value: K control steps of every drone in one launch ---------------------------------------------------------
     l0 = loop.solver.launch_count()
-    spl = max(1, args.steps_per_launch)
-    nl = (K + spl - 1) // spl
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nl)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
         t0 = time.perf_counter()
-        for i in range(nl):
-            if flush is not None:
-                flush.fill_(i & 0xff)             # evict L2 between timed launches (not timed)
-            evs[i][0].record(stream)
-            loop.run(min(spl, K - i * spl), steps_per_launch=spl)
-            evs[i][1].record(stream)
+        e0.record(stream)
+        loop.run(K, steps_per_launch=args.steps_per_launch or K)
+        e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
-    launches = loop.solver.launch_count() - l0
+        launches = loop.solver.launch_count() - l0
+        ms_multi = e0.elapsed_time(e1)
+        # ---- the same K steps as K launches (latency path), L2 flushed between launches ------------------------------
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        for i in range(K):
+            flush.fill_(i & 0xff)
+            evs[i][0].record(stream)
+            loop.run(1)
+            evs[i][1].record(stream)
+        barrier()
     step_ms = np.array([a.elapsed_time(b) for a, b in evs])
-    tot_ms = float(step_ms.sum())
-    tmax = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    tot_ms_all = float(tmax[0])
+    ms_multi_all, ms_step_all = allmax(ms_multi), allmax(float(step_ms.sum()))
+    value = world * B * K / (ms_multi_all * 1e-3)
     res = loop.results()
     qp = res['qp_iter'][:, W:W + K].double()
     st = res['status'][:, W:W + K]
-    stats = torch.tensor([float(qp.sum()), float((st != 0).sum()), float(res['cost'].sum()), float(res['aed'].sum()), float(B)],
-                         dtype=torch.float64, device=dev)
+    sqp_mean = float(loop.solver.get_stats('sqp_iter').double().mean())
+    stats = torch.tensor([float(qp.sum()), float((st != 0).sum()), float(res['cost'].sum()), float(res['aed'].sum()), float(B),
+                          float(res['failures'].sum())], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(stats)                    # the only collective: final per-step metrics (< 1 KB)
-    value = world * B * K / (tot_ms_all * 1e-3)
+        dist.all_reduce(stats)                    # the only collective of the headline: final per-step metrics (< 1 KB)
+    qp_local = float(qp.sum())
+    del loop, res
 
-    # ---- e2e: the AcadosOcpSolver-style call sequence with pinned host buffers, every step ---------------------------
+    # ---- e2e: the reference's loop shape through the shim with pinned host buffers, every step ------------------------
     e2e = None
     if not args.skip_e2e:
-        s = pkg.BatchedAcadosOcpSolver(args.model, batch=B, device=local, precision=args.precision, N_horizon=N, rti=args.rti,
-                                       numpy_io=False)
-        ny, nx, nu = s.ny, s.nx, s.nu
-        Ke = min(K, args.e2e_steps)
-        ref_h = ref_im.cpu()                                      # [B, rows, 8]
-        ycols = list(range(nx)) + [nx + j for j in range(nu)] if nx == 6 else [0, 1, 2, 3, 4, 5]
-        yh = [torch.cat([ref_h[:, i:i + N, ycols].reshape(B, N * ny), ref_h[:, i + N, :nx]], 1).contiguous().pin_memory()
-              for i in range(W + Ke)]
-        xs_log = res['Xsim'].cpu()                                 # states the fused loop visited: realistic x0 stream
-        acc0 = torch.tensor([0.0, 9.81], dtype=torch.float64).expand(B, 2)
-        x0h = [(xs_log[:, i, :] if nx == 4 else torch.cat([xs_log[:, i, :], acc0], 1)).contiguous().pin_memory() for i in range(W + Ke)]
-        u_host = torch.empty((B, nu), dtype=torch.float64).pin_memory()
-        st_host = torch.empty(B, dtype=torch.int32).pin_memory()
+        e2e = run_e2e(args, pkg, dev, local, inp, ref_im, world, barrier, allmax, min(K, args.e2e_steps))
+    del ref_im
+    torch.cuda.empty_cache()
 
-        per = N * ny + nx
-        ydev = [torch.empty((B, per), dtype=torch.float64, device=dev) for _ in range(2)]
-        yev = [torch.cuda.Event(), torch.cuda.Event()]
-        copy_stream = torch.cuda.Stream(device=dev)
-
-        def prefetch(i):      # upload the reference window of step i on the copy stream (overlaps the solve of step i-1)
-            with torch.cuda.stream(copy_stream):
-                ydev[i % 2].copy_(yh[i], non_blocking=True)
-                yev[i % 2].record(copy_stream)
-
-        def e2e_step(i, pipelined, last):
-            if pipelined:
-                torch.cuda.current_stream().wait_event(yev[i % 2])
-                s.set_yref_all(ydev[i % 2])
-                s.solve_for_x0_into(x0h[i], u_host, st_host, wait=False)   # enqueue: x0 in, solve, u0 + status out (pinned host)
-                if not last:
-                    prefetch(i + 1)      # behind this step's x0 on the H2D engine, concurrent with the solve
-                s.synchronize()          # u0 and status of this step are in host memory
-            else:
-                s.set_yref_all(yh[i])
-                s.solve_for_x0_into(x0h[i], u_host, st_host)    # returns when u0 + status are in host memory
-
-        def e2e_run(pipelined):
-            s.reset()
-            if pipelined:
-                prefetch(0)
-            for i in range(W):
-                e2e_step(i, pipelined, False)
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(W, W + Ke):
-                e2e_step(i, pipelined, i == W + Ke - 1)
-            barrier()
-            te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-            if world > 1:
-                dist.all_reduce(te, op=dist.ReduceOp.MAX)
-            return world * B * Ke / float(te[0])
-
-        e2e_serial = e2e_run(False)
-        e2e_pipe = e2e_run(True)
-        e2e = {'value': e2e_pipe, 'unit': UNIT, 'steps': Ke, 'serial_value': e2e_serial,
-               'h2d_bytes_per_step': int(B * (N * ny + nx + 2 * nx) * 8), 'd2h_bytes_per_step': int(B * (nu * 8 + 4)),
-               'api': 'BatchedAcadosOcpSolver.set_yref_all (OCP.set_up_ocp) + solve_for_x0 (x0 in, u0 and status out) with pinned host buffers, every step; '
-                      'value: x0 upload, solve and u0/status download are enqueued asynchronously, then the upload of the next step\'s '
-                      'reference window (known in advance) is enqueued on a copy stream and overlaps the solve, then the step waits; '
-                      'serial_value: everything on one stream'}
+    # ---- extra: BASELINE configs 3, 4, 5, bounded ---------------------------------------------------------------------
+    extra = None
+    if not args.skip_extra:
+        extra = run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range)
 
     if rank != 0:
         if world > 1:
@@ -244,107 +278,218 @@ def run_ours(args):
         pass
     tf = C.c_double()
     _lib.check(_lib.lib().bnmpc_measure_fma_peak(local, _lib.FP32 if args.precision == 'fp32' else _lib.FP64, C.byref(tf)))
-    dims = dict(force=(2, 2, 1, 4, 2, 4), jerk=(2, 3, 1, 6, 2, 1), force_dense=(1, 4, 2, 4, 2, 4), thrust=(1, 4, 2, 4, 2, 4))[args.model]
-    nblk, n, m, nx, nu, erk = dims
-    qp_local = float(qp.sum())
-    fl = flops_per_solve(nblk, n, m, N, erk, qp_local / (B * K)) * B                      # per launch, this rank
-    by = bytes_per_solve(nx, nu, N) * B
-    ms_launch = tot_ms / K
-    ach_tf = fl / (ms_launch * 1e-3) * 1e-12
-    ach_gbs = by / (ms_launch * 1e-3) * 1e-9
+    nblk, n, m, nx, nu, erk = MODEL_DIMS[args.model]
+    lin = 1.0 if args.rti else sqp_mean + 1.0
+    fl = flops_per_solve(nblk, n, m, N, erk, qp_local / (B * K), lin) * B * K       # per launch (K steps), this rank
+    by = bytes_per_solve(nx, nu, N) * B * K
+    ach_tf = fl / (ms_multi * 1e-3) * 1e-12
+    ach_gbs = by / (ms_multi * 1e-3) * 1e-9
     hbm_peak = peaks.get('hbm_gbs', 6650.0)
     traffic, ncu_view = None, None
     try:       # dram bytes per launch and pipe utilisation of the dominant kernel from the committed ncu capture of this config
-        ncu_view = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(f'{args.model}_{args.precision}_B{B}')
+        ncu_view = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(f'{args.model}_{args.precision}_B{B}_multistep')
         traffic = ncu_view.get('traffic_bytes') if ncu_view else None
     except Exception:
         pass
+    cfg = config_dict(args)
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': tot_ms_all / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic',
-        'config': {'workload': f'{args.model}_model batched closed loop, {B} drones per GPU with randomised x0 and circle trajectories '
-                               f'(BASELINE config 2), N_horizon {N}, {"SQP_RTI" if args.rti else "SQP to tol 1e-6"} + HPIPM-style IPM, '
-                               f'noise sigma 0.01',
-                   'batch_per_gpu': B, 'horizon': N, 'controller': args.model, 'plant_mass_sigma': args.mass_sigma,
-                   'reference': 'per-instance table [B, rows, 8] in HBM' if args.ref == 'table' else 'generated in the kernel (CircleRef)',
-                   'l2': 'flushed between timed steps (256 MiB write, untimed)' if args.flush_l2 else 'not flushed',
-                   'timing': 'sum of per-step CUDA-event durations on the launch stream, max over ranks'},
+        'ms_per_step': ms_multi_all / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic', 'config': cfg,
+        'launch_mode': f'value = {K} control steps of every drone in {launches} launch(es) (steps_per_launch = {args.steps_per_launch or K})',
+        'per_step_launch': {'value': world * B * K / (ms_step_all * 1e-3), 'unit': UNIT, 'ms_per_step': ms_step_all / K,
+                            'p50_step_latency_ms': float(np.median(step_ms)), 'p99_step_latency_ms': float(np.percentile(step_ms, 99)),
+                            'gpu_launches': K},
         'p50_step_latency_ms': float(np.median(step_ms)), 'p99_step_latency_ms': float(np.percentile(step_ms, 99)),
-        'qp_iter_mean': float(stats[0]) / (world * B * K), 'nonzero_status': int(stats[1]),
+        'qp_iter_mean': float(stats[0]) / (world * B * K), 'sqp_iter_mean': sqp_mean, 'nonzero_status': int(stats[1]),
+        'failed_steps_whole_run': int(stats[5]),
         'closed_loop_cost_mean': float(stats[2]) / float(stats[4]), 'aed_mean': float(stats[3]) / float(stats[4]),
         'gpu_launches': int(launches), 'wall_s_timed_region': wall,
         'clocks': clk.summary(),
         'e2e': e2e,
         'roofline': {'bound': 'fp64' if args.precision == 'fp64' else 'fp32', 'achieved': ach_tf, 'peak': tf.value, 'unit': 'TFLOP/s',
                      'frac': ach_tf / tf.value if tf.value else None, 'traffic': traffic,
-                     'peak_source': 'measured live: bnmpc_measure_fma_peak (MEASURED_PEAKS.json has no vector-pipe figure)',
-                     'kernel': 'k_loop_step', 'flops_per_launch': fl, 'ms_per_launch': ms_launch, 'ncu': ncu_view,
+                     'peak_source': 'measured live: bnmpc_measure_fma_peak (MEASURED_PEAKS.json has no vector-pipe figure); '
+                                    'a recorded copy with its clock record is profiles/fma_peak.json',
+                     'kernel': 'k_loop_step', 'flops_per_launch': fl, 'ms_per_launch': ms_multi,
+                     'linearisations_per_solve': lin, 'ncu': ncu_view,
                      'hbm': {'bound': 'hbm', 'achieved': ach_gbs, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': ach_gbs / hbm_peak,
                              'bytes_per_launch': by,
                              'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if 'hbm_gbs' in peaks else 'fallback 6650'}},
+        'extra': extra,
     }
     if not args.skip_cpu and world == 1:
-        line['cpu_baseline'] = cpu_baseline(args, sample_instances=args.cpu_instances, sample_steps=args.cpu_steps)
+        n_inst = min(args.cpu_instances, B)
+        dt, qpm, bad, cores, flags = cpu_closed_loop(args, inp, n_inst, W, args.cpu_steps)
+        dense_ratio = flops_per_solve(1, nx, nu, N, erk, 1, 0) / flops_per_solve(nblk, n, m, N, erk, 1, 0)
+        line['cpu_baseline'] = {'value': n_inst * args.cpu_steps / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'qp_iter_mean': qpm, 'nonzero_status': bad,
+                                'sample': f'the first {n_inst} of the workload\'s instances (same global ids, same inputs) x {args.cpu_steps} '
+                                          f'closed-loop steps after {W} warm-up steps, oracle/nmpc_oracle.c built {flags}, {cores} pthreads, '
+                                          f'{dt:.1f} s; the port factorises dense {nx}-state stages (no x/z block split: '
+                                          f'{dense_ratio:.1f}x the flops per IPM iteration of the GPU path)'}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_inputs(args, B, S):
-    from oracle import nmpc_oracle as o
-    rng = np.random.default_rng(2026)
-    N = args.horizon
-    refs = np.stack([o.gen_circle_traj(n_horizon=max(N, 30), radius=rng.uniform(0.5, 1.0), center=rng.uniform(-0.15, 0.15, 2),
-                                       phase=rng.uniform(0, 2 * np.pi)) for _ in range(B)])
-    x0 = refs[:, 0, :4] + rng.uniform(-0.05, 0.05, (B, 4))
-    noise = rng.normal(0, 0.01, (S, B))
-    pp = np.repeat(np.array([[o.MASS, o.GRAVITY_ACC]]), B, 0)
-    return refs, x0, noise, pp
+def run_e2e(args, pkg, dev, local, inp, ref_im, world, barrier, allmax, Ke):
+    """follow_trajectory of the reference (src/force_model/controller.py:25-54 / src/jerk_model/controller.py:26-56) for the
+    whole batch through the AcadosOcpSolver-style shim, host buffers in and out every step:
+        set_up_ocp (yref window H2D) -> set x0 (H2D) -> solve -> get u0, status (D2H) -> Converter on the host ->
+        simulate_next_x (x, u, noise H2D; x_next D2H) -> next step's x0.
+    The window of step i+1 is known in advance, so its upload is enqueued on a copy stream behind step i's x0 and overlaps
+    the solve; everything that depends on the solution is serial, as in the reference."""
+    import torch
+    B, N, W = args.batch, args.horizon, args.warmup
+    s = pkg.BatchedAcadosOcpSolver(args.model, batch=B, device=local, precision=args.precision, N_horizon=N, rti=args.rti, numpy_io=False)
+    ny, nx, nu = s.ny, s.nx, s.nu
+    jerk = nx == 6
+    nsub = int(s.cfg.sim_substeps)
+    hc = float(s.cfg.sim_dt)
+    ref_h = ref_im.cpu()                                      # [B, rows, 8]
+    ycols = list(range(nx)) + [nx + j for j in range(nu)] if jerk else [0, 1, 2, 3, 4, 5]
+    yh = [torch.cat([ref_h[:, i:i + N, ycols].reshape(B, N * ny), ref_h[:, i + N, :nx]], 1).contiguous().pin_memory()
+          for i in range(W + Ke)]
+    noise_h = inp['noise'][:W + Ke].contiguous().pin_memory()      # [steps, B]
+    pin = lambda *sh, dt=torch.float64: torch.empty(sh, dtype=dt).pin_memory()
+    x0h, u_host, st_host = pin(B, nx), pin(B, nu), pin(B, dt=torch.int32)
+    xs_h, up_h, xn_h = pin(B, 4), pin(B, nsub, 2), pin(B, 4)
+    acc = torch.zeros(B, 2, dtype=torch.float64)
+    per = N * ny + nx
+    ydev = [torch.empty((B, per), dtype=torch.float64, device=dev) for _ in range(2)]
+    yev = [torch.cuda.Event(), torch.cuda.Event()]
+    copy_stream = torch.cuda.Stream(device=dev)
+    mass = 0.03277
 
+    def prefetch(i):      # upload the reference window of step i on the copy stream (overlaps the solve of step i-1)
+        with torch.cuda.stream(copy_stream):
+            ydev[i % 2].copy_(yh[i], non_blocking=True)
+            yev[i % 2].record(copy_stream)
 
-def cpu_baseline(args, sample_instances, sample_steps):
-    """The oracle (CPU restatement, kind 'port': acados itself cannot be installed here) on the host cores."""
-    from oracle import c_oracle as co
-    model = co.MODEL_JERK if args.model.startswith('jerk') else co.MODEL_FORCE
-    cores = co.lib().orc_num_cores()
-    refs, x0, noise, pp = cpu_inputs(args, sample_instances, sample_steps)
-    opts = co.default_opts(model, N=args.horizon, rti=args.rti)
-    co.closed_loop(opts, refs[:cores], x0[:cores], noise[:2, :cores], pp[:cores], pp[:cores], 2, outputs=False)     # warm
+    def start():
+        s.reset()
+        xs_h.copy_(inp['x0'].t())
+        acc[:, 0] = 0.0; acc[:, 1] = 9.81
+        prefetch(0)
+
+    def step(i, last):
+        torch.cuda.current_stream().wait_event(yev[i % 2])
+        s.set_yref_all(ydev[i % 2])                                      # OCP.set_up_ocp
+        x0h[:, :4] = xs_h
+        if jerk:
+            x0h[:, 4:] = acc
+        s.solve_for_x0_into(x0h, u_host, st_host, wait=False)           # x0 in, solve, u0 + status out (pinned host)
+        if not last:
+            prefetch(i + 1)
+        s.synchronize()
+        if jerk:                                                         # Converter.convert, jerk dynamics.py:76-83
+            for j in range(nsub):
+                acc.add_(u_host, alpha=hc)
+                f = mass * acc
+                up_h[:, j, 0] = torch.atan2(f[:, 0], f[:, 1]); up_h[:, j, 1] = torch.sqrt(f[:, 0] ** 2 + f[:, 1] ** 2)
+        else:                                                            # dynamics.py:66-70
+            up_h[:, 0, 0] = torch.atan2(u_host[:, 0], u_host[:, 1]); up_h[:, 0, 1] = torch.sqrt(u_host[:, 0] ** 2 + u_host[:, 1] ** 2)
+        s.simulate_next_x_into(xs_h, up_h, noise_h[i], xn_h, wait=True)  # OCP.simulate_next_x incl. the noise draw
+        xs_h.copy_(xn_h)
+
+    start()
+    for i in range(W):
+        step(i, False)
+    barrier()
     t0 = time.perf_counter()
-    co.closed_loop(opts, refs, x0, noise, pp, pp, sample_steps, nthreads=cores, outputs=False)
-    dt = time.perf_counter() - t0
-    return {'value': sample_instances * sample_steps / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': f'{sample_instances} of the workload\'s instances x {sample_steps} closed-loop steps, oracle/nmpc_oracle.c, '
-                      f'{cores} pthreads, {dt:.1f} s'}
+    for i in range(W, W + Ke):
+        step(i, i == W + Ke - 1)
+    barrier()
+    dt = allmax(time.perf_counter() - t0)
+    bad = int((st_host != 0).sum())
+    return {'value': world * B * Ke / dt, 'unit': UNIT, 'steps': Ke, 'ms_per_step': dt / Ke * 1e3,
+            'h2d_bytes_per_step': int(B * (per + nx + 4 + 2 * nsub + 1) * 8), 'd2h_bytes_per_step': int(B * (nu * 8 + 4 + 4 * 8)),
+            'nonzero_status_last_step': bad,
+            'api': 'per step: BatchedAcadosOcpSolver.set_yref_all (OCP.set_up_ocp) + solve_for_x0 (x0 in, u0 and status out) + Converter on '
+                   'the host + simulate_next_x (x, u, noise in, x_next out), pinned host buffers; the upload of the next step\'s reference '
+                   'window (known in advance) rides a copy stream behind this step\'s x0 and overlaps the solve'}
+
+
+def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):
+    """Bounded runs of BASELINE configs 3, 4, 5 with the multi-step launch path (inputs resident, circle reference generated in
+    the kernel, noise drawn in the kernel by Philox): solves/s, statuses, algorithmic roofline fraction."""
+    import ctypes as C
+    import torch
+    from drone_attitude_control_b200 import _lib
+    from drone_attitude_control_b200.sharding import instance_inputs
+    peak = {}
+
+    def fma_peak(prec):
+        if prec not in peak:
+            tf = C.c_double()
+            _lib.check(_lib.lib().bnmpc_measure_fma_peak(local, _lib.FP32 if prec == 'fp32' else _lib.FP64, C.byref(tf)))
+            peak[prec] = tf.value
+        return peak[prec]
+
+    def one(model, total, N, prec, steps, warm, mass_sigma, sharded):
+        lo, hi = shard_range(total, rank, world) if sharded else (rank * total, (rank + 1) * total)
+        b = hi - lo
+        inp = instance_inputs(lo, hi, 0, seed=SEED, mass_sigma=mass_sigma, with_noise=False)
+        om = 2 * np.pi / 10
+        cref = pkg.CircleRef(inp['radius'], inp['center'], inp['phase'], n=500)
+        r, ph, c = inp['radius'], inp['phase'], inp['center']
+        x0 = torch.stack([c[:, 0] + r * torch.cos(ph), c[:, 1] + r * torch.sin(ph), -r * om * torch.sin(ph), r * om * torch.cos(ph)]) + inp['dx0']
+        loop = pkg.BatchedClosedLoop(model, batch=b, device=local, precision=prec, N_horizon=N)
+        pp = torch.stack([0.03277 * inp['mass_scale'], torch.full((b,), 9.81, dtype=torch.float64)]) if mass_sigma > 0 else None
+        loop.init(x0, cref, noise=pkg.PhiloxNoise(seed=SEED, std=0.01, first_instance=lo), p_plant=pp, n_steps=warm + steps, log=False)
+        loop.run(warm, steps_per_launch=warm)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); loop.run(steps, steps_per_launch=steps); e1.record()
+        barrier()
+        ms = allmax(e0.elapsed_time(e1))
+        qp = loop.solver.get_stats('qp_iter').double()
+        sq = loop.solver.get_stats('sqp_iter').double()
+        st = torch.tensor([float(loop.failures().sum()), float(qp.sum()), float(sq.sum()), float(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(st)
+        tot = int(st[3])
+        nblk, n, m, nx, nu, erk = MODEL_DIMS[model]
+        fl = flops_per_solve(nblk, n, m, N, erk, float(st[1]) / tot, float(st[2]) / tot + 1.0) * tot * steps
+        ach = fl / (ms * 1e-3) * 1e-12
+        del loop
+        torch.cuda.empty_cache()
+        return {'model': model, 'instances_total': tot, 'instances_this_rank': b, 'sharded_over_ranks': bool(sharded), 'horizon': N,
+                'precision': prec, 'steps': steps, 'warmup': warm, 'ms': ms, 'value': tot * steps / (ms * 1e-3), 'unit': UNIT,
+                'failed_steps': int(st[0]), 'qp_iter_mean_last_step': float(st[1]) / tot,
+                'roofline_frac': ach / fma_peak(prec), 'achieved_tflops': ach}
+
+    out = {'note': 'multi-step launches (steps_per_launch = steps), CircleRef + PhiloxNoise generated in the kernel, CUDA events, max over ranks'}
+    out['config3_jerk_16384_fp64'] = one('jerk', 16384, 30, 'fp64', 20, 5, 0.0, False)
+    out['config3_jerk_16384_fp32'] = one('jerk', 16384, 30, 'fp32', 20, 5, 0.0, False)
+    out['config4_force_262144_mass_perturbed_sharded'] = dict(one('force', 262144, 30, 'fp64', 10, 3, 0.05, True), scaling='strong')
+    for N in (20, 50, 100):
+        out[f'config5_force_65536_N{N}'] = one('force', 65536, N, 'fp64', 4 if N > 30 else 8, 2, 0.0, False)
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement of the reference's path on the host cores, same metric and config."""
+    """--impl reference: the CPU restatement of the reference's path on the host cores, same metric, same config, same
+    instances (sharding.instance_inputs of the same global ids), a bounded sample per step."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    from oracle import c_oracle as co
-    model = co.MODEL_JERK if args.model.startswith('jerk') else co.MODEL_FORCE
-    cores = co.lib().orc_num_cores()
-    K, W = args.steps, args.warmup
+    K, W, N = args.steps, args.warmup, args.horizon
     Bs = min(args.cpu_instances, args.batch)
-    refs, x0, noise, pp = cpu_inputs(args, Bs, W + K)
-    opts = co.default_opts(model, N=args.horizon, rti=args.rti)
-    # warm-up steps, then K timed steps continuing the same closed loop (the oracle API runs whole loops: time the
-    # (W+K)-step run and the W-step run and subtract)
-    t0 = time.perf_counter(); co.closed_loop(opts, refs, x0, noise, pp, pp, W, nthreads=cores, outputs=False); tw = time.perf_counter() - t0
-    t0 = time.perf_counter(); co.closed_loop(opts, refs, x0, noise, pp, pp, W + K, nthreads=cores, outputs=False); tk = time.perf_counter() - t0
-    dt = max(tk - tw, 1e-9)
+    rows = max(500 + N, W + K + N + 1)
+    inp = workload(0, Bs, W + K, rows, N, mass_sigma=args.mass_sigma)
+    dt, qpm, bad, cores, flags = cpu_closed_loop(args, inp, Bs, W, K)
     value = Bs * K / dt
     world = int(os.environ.get('WORLD_SIZE', '1'))
-    sample = f'{Bs} of the workload\'s {args.batch} instances per step, oracle/nmpc_oracle.c, {cores} pthreads'
+    sample = (f'the first {Bs} of the workload\'s {args.batch} instances per step (same global ids and inputs as the GPU arm), '
+              f'oracle/nmpc_oracle.c built {flags}, {cores} pthreads')
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
-        'ms_per_step': dt / K * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': f'{args.model}_model batched closed loop (BASELINE config 2), N_horizon {args.horizon}; CPU restatement of the '
-                               f'reference path (acados is not installable here), bounded sample', 'batch_per_gpu': args.batch,
-                   'horizon': args.horizon, 'controller': args.model},
+        'ms_per_step': dt / K * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f64' if args.precision == 'fp64' else 'f32', 'data': 'synthetic', 'config': config_dict(args),
+        'qp_iter_mean': qpm, 'nonzero_status': bad,
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0}))
@@ -363,13 +508,13 @@ def main():
     ap.add_argument('--rti', action='store_true')
     ap.add_argument('--ref', default='table', choices=['table', 'circle'], help='trajectory table in HBM, or generated in the kernel')
     ap.add_argument('--mass-sigma', type=float, default=0.0, help='BASELINE config 4: plant mass = 0.03277 (1 + N(0, sigma)) clipped to +-15 %%')
-    ap.add_argument('--steps-per-launch', type=int, default=1)
-    ap.add_argument('--no-flush-l2', dest='flush_l2', action='store_false')
+    ap.add_argument('--steps-per-launch', type=int, default=0, help='control steps per launch of the `value` leg (default: all K in one launch)')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu', action='store_true')
+    ap.add_argument('--skip-extra', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=50)
     ap.add_argument('--cpu-instances', type=int, default=4096)
-    ap.add_argument('--cpu-steps', type=int, default=300, help='closed-loop steps of the cpu_baseline sample (~10 s on 16 cores)')
+    ap.add_argument('--cpu-steps', type=int, default=60, help='closed-loop steps of the cpu_baseline sample (~10-20 s of CPU work)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libbnmpc.so')
+LIB_PATH = os.environ.get('BNMPC_LIB') or os.path.join(_HERE, 'lib', 'libbnmpc.so')      # BNMPC_LIB: another build of the same library (A/B timing)
 
 MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_THRUST = 0, 1, 2, 3
 MODELS = {'force': MODEL_FORCE, 'jerk': MODEL_JERK, 'force_dense': MODEL_FORCE_DENSE, 'thrust': MODEL_THRUST}

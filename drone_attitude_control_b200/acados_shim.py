@@ -204,6 +204,15 @@ class BatchedAcadosOcpSolver:
         check(lib().bnmpc_solve_for_x0(self._h, C.c_void_p(x0_dev.data_ptr()), C.c_void_p(u0_dev.data_ptr()),
                                        C.c_void_p(status_dev.data_ptr()), 1))
 
+    def simulate_next_x_into(self, x_host, u_host, eps_host, xn_host, p_plant_host=None, wait=True):
+        """OCP.simulate_next_x (src/force_model/ocp.py:106-115, src/jerk_model/ocp.py:106-116) for all drones with the plant
+        integrator this OCP was configured with (AcadosSim of create_simulator): pinned host tensors x [B, 4], u [B, substeps,
+        2] = (theta, Fd) per sub-step, eps [B] (the noise draw, or None) in, x_next [B, 4] out.  wait=False only enqueues."""
+        nsub = int(u_host.shape[1]) if u_host.dim() == 3 else 1
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(lib().bnmpc_sim_step(self._h, nsub, ptr(x_host), ptr(u_host), ptr(p_plant_host), ptr(eps_host), ptr(xn_host),
+                                   0 if wait else 2))
+
     def get_cost(self):
         """acados get_cost(): the NLP objective at the current iterate (LINEAR_LS, stage cost scaled by dt)."""
         io, self.numpy_io = self.numpy_io, False

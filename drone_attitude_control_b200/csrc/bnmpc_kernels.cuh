@@ -278,13 +278,12 @@ k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, co
     const WarpGroup<32> g;
     const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
     Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
-    if (a.n_steps <= 1) {
-        for (int inst = next_instance(queue, o.order, gs.B); inst < gs.B; inst = next_instance(queue, o.order, gs.B)) closed_loop_step<M, T>(sv, inst, gs, a);
-    } else {      // tickets = (instance, chunk of control steps), issued instance-round-robin
-        DevTickets wq{queue, a.next_step};
-        const int total = gs.B * ((a.n_steps + a.chunk - 1) / a.chunk);
-        for (int t = wq.take(); t < total; t = wq.take()) closed_loop_chunk<M, T>(sv, t, gs, a, wq);
-    }
+    // queue tickets = (instance, chunk of control steps), issued instance-round-robin; with one control step per launch a
+    // ticket is simply an instance (one copy of the solver code for both cases: the kernel's hot loop is instruction-fetch
+    // sensitive, see profiles/README.md)
+    DevTickets wq{queue, a.next_step};
+    const int total = gs.B * ((a.n_steps + a.chunk - 1) / a.chunk);
+    for (int t = wq.take(); t < total; t = wq.take()) closed_loop_chunk<M, T>(sv, t, gs, a, wq);
     tmem_free_cta(tbase, tmem_cols);
 }
 
@@ -295,6 +294,7 @@ k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, co
 // one lane of the sweep warp: it serves block `b` of the instance of warp slot `slot`
 struct SweepLane {
     static constexpr int L = 1;
+    static constexpr bool PAR_SCAN = false;
     int lane;
     __device__ __forceinline__ SweepLane() : lane(0) {}
     template <class T> __device__ __forceinline__ T max(T v) const { return v; }

@@ -16,28 +16,71 @@ def shard_range(batch, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def instance_inputs(lo, hi, n_steps, seed=2026, x0_spread=0.05, noise_std=0.01, mass_sigma=0.0):
-    """BASELINE config 2 / 4 inputs for global instances lo..hi-1 (float64, CPU tensors, batch-minor):
-    radius [b], center [b,2], phase [b] of the circle reference, dx0 [4,b] offset of the start state from the
-    reference, noise [n_steps,b], mass_scale [b] (plant mass = 0.03277 * mass_scale).
-    Every instance draws from its own generator seeded by (seed, global id), so any sharding gives the same numbers."""
-    b = hi - lo
-    radius = torch.empty(b, dtype=torch.float64); center = torch.empty(b, 2, dtype=torch.float64)
-    phase = torch.empty(b, dtype=torch.float64); dx0 = torch.empty(4, b, dtype=torch.float64)
-    noise = torch.empty(n_steps, b, dtype=torch.float64); mass = torch.ones(b, dtype=torch.float64)
-    g = torch.Generator()
-    for j, gid in enumerate(range(lo, hi)):
-        g.manual_seed(int(seed) * 1000003 + gid)
-        u = torch.rand(8, generator=g, dtype=torch.float64)
-        radius[j] = 0.5 + 0.5 * u[0]
-        center[j] = -0.15 + 0.3 * u[1:3]
-        phase[j] = 2 * np.pi * u[3]
-        dx0[:, j] = x0_spread * (2 * u[4:8] - 1)
-        z = torch.randn(n_steps + 1, generator=g, dtype=torch.float64)
-        noise[:, j] = noise_std * z[:n_steps]
-        if mass_sigma > 0:
-            mass[j] = 1 + float(torch.clamp(mass_sigma * z[n_steps], -0.15, 0.15))
-    return dict(radius=radius, center=center, phase=phase, dx0=dx0, noise=noise, mass_scale=mass)
+_M32 = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 (Salmon et al., SC'11) on arrays of counters; the host mirror of philox4x32_10 in csrc/bnmpc_loop.cuh.
+    Inputs are integer arrays / scalars (32-bit values), outputs four uint64 arrays holding 32-bit words."""
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) & _M32 for c in (c0, c1, c2, c3))
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0, k1 = np.uint64(int(k0) & 0xFFFFFFFF), np.uint64(int(k1) & 0xFFFFFFFF)
+    m0, m1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+    for _ in range(10):
+        p0, p1 = m0 * c0, m1 * c2
+        c0, c1, c2, c3 = (p1 >> np.uint64(32)) ^ c1 ^ k0, p1 & _M32, (p0 >> np.uint64(32)) ^ c3 ^ k1, p0 & _M32
+        k0, k1 = (k0 + np.uint64(0x9E3779B9)) & _M32, (k1 + np.uint64(0xBB67AE85)) & _M32
+    return c0, c1, c2, c3
+
+
+def _uniform53(hi, lo, open_left=False):
+    """53-bit uniform from two 32-bit words: [0, 1), or (0, 1] with open_left (the argument of a logarithm)"""
+    v = ((hi << np.uint64(32)) | lo) >> np.uint64(11)
+    return (v + np.uint64(1 if open_left else 0)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def philox_uniforms(seed, gid, block, stream):
+    """two uniforms in [0, 1) per element of `gid` from the Philox block with counter (gid, block, stream)"""
+    gid = np.asarray(gid, dtype=np.uint64)
+    r = philox4x32_10(gid & _M32, gid >> np.uint64(32), block, stream, int(seed) & 0xFFFFFFFF, int(seed) >> 32)
+    return _uniform53(r[0], r[1]), _uniform53(r[2], r[3])
+
+
+def philox_normal(seed, gid, step, stream=0):
+    """N(0,1) of (seed, global instance, step): the host mirror of philox_normal in csrc/bnmpc_loop.cuh (Box-Muller on the two
+    53-bit uniforms of the block with counter (instance, step, stream)); equal to the device draw up to the rounding of the
+    device's log / cos."""
+    gid = np.asarray(gid, dtype=np.uint64)
+    r = philox4x32_10(gid & _M32, gid >> np.uint64(32), step, stream, int(seed) & 0xFFFFFFFF, int(seed) >> 32)
+    u1, u2 = _uniform53(r[0], r[1], open_left=True), _uniform53(r[2], r[3])
+    return np.sqrt(-2.0 * np.log(u1)) * np.cos(6.283185307179586476925 * u2)
+
+
+def instance_inputs(lo, hi, n_steps, seed=2026, x0_spread=0.05, noise_std=0.01, mass_sigma=0.0, with_noise=True):
+    """BASELINE config 2 / 4 inputs (SURVEY 8d) for global instances lo..hi-1 (float64, CPU tensors, batch-minor):
+    radius [b] in [0.5, 1], center [b,2] in [-0.15, 0.15]^2, phase [b] in [0, 2 pi) of the circle reference, dx0 [4,b] offset
+    of the start state from the reference (+-x0_spread), noise [n_steps,b] (None unless with_noise), mass_scale [b] (plant
+    mass = 0.03277 * mass_scale, 1 + N(0, mass_sigma) clipped to +-15 %).
+    Every number is a counter-based draw keyed by (seed, GLOBAL instance id[, step]) - Philox4x32-10, vectorised over the
+    instances - so any sharding of the batch gives the same numbers, and the noise equals what the kernel draws itself when
+    the loop is given a PhiloxNoise(seed, noise_std, first_instance=lo) instead of the array."""
+    gid = np.arange(lo, hi, dtype=np.uint64)
+    u_r, u_ph = philox_uniforms(seed, gid, 0, 1)
+    u_cx, u_cz = philox_uniforms(seed, gid, 1, 1)
+    u_a, u_b = philox_uniforms(seed, gid, 2, 1)
+    u_c, u_d = philox_uniforms(seed, gid, 3, 1)
+    radius = 0.5 + 0.5 * u_r
+    center = np.stack([-0.15 + 0.3 * u_cx, -0.15 + 0.3 * u_cz], 1)
+    phase = 2 * np.pi * u_ph
+    dx0 = x0_spread * (2 * np.stack([u_a, u_b, u_c, u_d], 0) - 1)
+    mass = np.ones(hi - lo)
+    if mass_sigma > 0:
+        mass = 1 + np.clip(mass_sigma * philox_normal(seed, gid, 4, stream=1), -0.15, 0.15)
+    noise = None
+    if with_noise:
+        noise = noise_std * philox_normal(seed, gid[None, :], np.arange(n_steps, dtype=np.uint64)[:, None])
+    t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    return dict(radius=t(radius), center=t(center), phase=t(phase), dx0=t(dx0), noise=t(noise), mass_scale=t(mass))
 
 
 def reduce_metrics(values, op='sum', group=None):

@@ -74,8 +74,12 @@ typedef struct bnmpc_config {
     int32_t model;          /* BNMPC_MODEL_* */
     int32_t horizon;        /* N_horizon (reference src/params.py:121) */
     int32_t precision;      /* BNMPC_FP64 | BNMPC_FP32 */
-    int32_t erk_stages;     /* OCP integrator stages, one step per interval: force 4 (stands in for IRK: exact for the
-                               affine model, src/force_model/ocp.py:85), jerk 1 (src/jerk_model/ocp.py:86-87) */
+    int32_t erk_stages;     /* OCP integrator, one step per interval.  1..4: explicit Runge-Kutta with that many stages (acados
+                               ERK + sim_method_num_stages; jerk 1, src/jerk_model/ocp.py:86-87).  0: acados IRK with its
+                               defaults - Gauss-Legendre collocation, 4 stages, 3 Newton iterations, sensitivities by the
+                               implicit function theorem - the integrator_type of the force OCP (src/force_model/ocp.py:85).
+                               The default of the force model is 4: for its affine dynamics ERK4 and the collocation both
+                               return the exact discretisation (tests: equal to 1e-14), at a fraction of the work */
     int32_t sqp_max_iter;   /* acados nlp_solver_max_iter default 100 (nlp_solver_type SQP, src/force_model/ocp.py:86) */
     int32_t qp_max_iter;    /* acados qp_solver_iter_max default 50 */
     int32_t rti;            /* 1: one QP per solve, no NLP residual test (SQP_RTI of the north-star) */
@@ -137,7 +141,9 @@ int bnmpc_get_stats(void* handle, int which, int32_t* out, int on_device);
  * in a row as OCP.simulate_next_x of the jerk path does (src/jerk_model/ocp.py:106-113): each sub-step is one ERK step
  * (sim_erk_stages stages) of length sim_dt with its own input.
  * x AoS [batch][4], u AoS [batch][substeps][2] = (theta, Fd) per sub-step, p_plant AoS [batch][2] or NULL (nominal),
- * eps [batch] or NULL added to all states of an instance at the end (the np.random.normal draw, :114-115). */
+ * eps [batch] or NULL added to all states of an instance at the end (the np.random.normal draw, :114-115).
+ * on_device as for bnmpc_solve_for_x0: 0 host buffers (returns with x_next in host memory), 1 device buffers (asynchronous),
+ * BNMPC_HOST_ASYNC pinned host buffers, copies and kernel enqueued, the caller synchronises. */
 int bnmpc_sim_step(void* handle, int substeps, const double* x, const double* u, const double* p_plant, const double* eps,
                    double* x_next, int on_device);
 

@@ -41,6 +41,13 @@ def lib():
     return _lib
 
 
+def load_variant(path):
+    """another build of the same source (bench.py: -march=native with compile-time dimensions, for timing)"""
+    L = C.CDLL(path)
+    assert L.orc_sizeof_opts() == C.sizeof(Opts)
+    return L
+
+
 def default_opts(model, N=30, rti=False, **kw):
     o = Opts()
     lib().orc_default_opts(C.c_int(model), C.byref(o))
@@ -89,7 +96,7 @@ def sim_batch(x, u, p, ns, nsub, T):
     return xn
 
 
-def closed_loop(o, ref, x0, noise, p_ctrl, p_plant, n_steps, nthreads=0, outputs=True):
+def closed_loop(o, ref, x0, noise, p_ctrl, p_plant, n_steps, nthreads=0, outputs=True, L=None):
     """ref [B,rows,8] or [rows,8] (shared); x0 [B,4]; noise [n_steps,B] or None; p_* [B,2]."""
     B = x0.shape[0]
     ref = np.ascontiguousarray(ref, float)
@@ -102,7 +109,7 @@ def closed_loop(o, ref, x0, noise, p_ctrl, p_plant, n_steps, nthreads=0, outputs
     if outputs:
         out.update(Xsim=np.zeros((B, n_steps + 1, 4)), U_plant=np.zeros((B, n_steps, 2)), U_ctrl=np.zeros((B, n_steps, 2)),
                    a=np.zeros((B, n_steps, 2)), status=np.zeros((B, n_steps), np.int32), qp_iter=np.zeros((B, n_steps), np.int32))
-    rc = lib().orc_closed_loop(C.byref(o), B, n_steps, rows, _dp(ref), int(shared), _dp(x0), _dp(noise), _dp(p_ctrl),
+    rc = (L or lib()).orc_closed_loop(C.byref(o), B, n_steps, rows, _dp(ref), int(shared), _dp(x0), _dp(noise), _dp(p_ctrl),
                                _dp(p_plant), _dp(out.get('Xsim')), _dp(out.get('U_plant')), _dp(out.get('U_ctrl')),
                                _dp(out.get('a')), _dp(out['cost']), _ip(out.get('status')), _ip(out.get('qp_iter')), nthreads)
     assert rc == 0, rc

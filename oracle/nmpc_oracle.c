@@ -35,7 +35,7 @@ enum { MODEL_FORCE = 0, MODEL_JERK = 1, MODEL_PLANT = 2 };
 typedef struct {
     int model;         /* MODEL_FORCE | MODEL_JERK */
     int N;             /* horizon */
-    int erk_stages;    /* OCP integrator: 4 (force; stands in for IRK, exact for the affine model), 1 (jerk) */
+    int erk_stages;    /* OCP integrator: 4 (force; stands in for IRK, exact for the affine model), 1 (jerk); 0 = IRK (irk_gl4_step) */
     int sqp_max_iter;  /* acados nlp_solver_max_iter (100) */
     int qp_max_iter;   /* acados qp_solver_iter_max (50) */
     int rti;           /* 1: exactly one QP per call, no NLP residual test (SQP_RTI) */
@@ -48,8 +48,19 @@ typedef struct {
     double mu0, thr0, alpha_min, lam_min, t_min;
 } orc_opts;
 
+/* Timing builds of bench.py fix the dimensions at compile time (-DORC_FIXED_NX=4 -DORC_FIXED_NU=2 ...) so that the
+ * compiler unrolls and vectorises the stage kernels; the default build reads them from the model at run time.  Same
+ * arithmetic either way. */
+#ifdef ORC_FIXED_NX
+#define ORC_NX(v) ORC_FIXED_NX
+#define ORC_NU(v) ORC_FIXED_NU
+#else
+#define ORC_NX(v) (v)
+#define ORC_NU(v) (v)
+#endif
+
 static void model_dims(int model, int *nx, int *nu) {
-    if (model == MODEL_JERK) { *nx = 6; *nu = 2; } else { *nx = 4; *nu = 2; }
+    if (model == MODEL_JERK) { *nx = ORC_NX(6); *nu = ORC_NU(2); } else { *nx = ORC_NX(4); *nu = ORC_NU(2); }
 }
 
 /* xdot = f(x,u,p), p = (mass, g) */
@@ -114,6 +125,78 @@ static void erk_step(int model, const double *x0, const double *u, const double 
     memcpy(xn, x, sizeof(double) * nx);
 }
 
+
+/* acados sim_irk restated (integrator_type 'IRK', reference src/force_model/ocp.py:85; same algorithm as
+ * oracle/nmpc_oracle.py irk_gl4_step): Gauss-Legendre collocation with 4 stages, Newton from K = 0 with the exact Jacobian
+ * I - h (A (x) f_x) re-evaluated in each of 3 iterations (dense LU, partial pivoting), sensitivities from the implicit
+ * function theorem at the final iterate.  Parity unpinned beyond the affine case (for which it is the exact discretisation). */
+static const double GL4_A[4][4] = {
+    {0.086963711284363464343, -0.026604180084998793313, 0.012627462689404724515, -0.0035551496857956831569},
+    {0.18811811749986807165, 0.16303628871563653566, -0.027880428602470895224, 0.0067355005945381555154},
+    {0.16719192197418877317, 0.35395300603374396654, 0.16303628871563653566, -0.014190694931141142964},
+    {0.17748257225452261184, 0.3134451147418683468, 0.35267675751627186463, 0.086963711284363464343}};
+static const double GL4_B[4] = {0.17392742256872692869, 0.32607257743127307131, 0.32607257743127307131, 0.17392742256872692869};
+
+static void lu_solve(int D, double *G, double *R, int ldr, int nrhs) {
+    for (int c = 0; c < D; c++) {
+        int pv = c; double best = fabs(G[c * D + c]);
+        for (int r = c + 1; r < D; r++) if (fabs(G[r * D + c]) > best) { best = fabs(G[r * D + c]); pv = r; }
+        if (pv != c) {
+            for (int j = 0; j < D; j++) { double t = G[c * D + j]; G[c * D + j] = G[pv * D + j]; G[pv * D + j] = t; }
+            for (int j = 0; j < nrhs; j++) { double t = R[c * ldr + j]; R[c * ldr + j] = R[pv * ldr + j]; R[pv * ldr + j] = t; }
+        }
+        const double inv = 1.0 / G[c * D + c];
+        for (int r = c + 1; r < D; r++) {
+            const double l = G[r * D + c] * inv;
+            if (l == 0.0) continue;
+            for (int j = c + 1; j < D; j++) G[r * D + j] -= l * G[c * D + j];
+            for (int j = 0; j < nrhs; j++) R[r * ldr + j] -= l * R[c * ldr + j];
+        }
+    }
+    for (int c = D - 1; c >= 0; c--) {
+        const double inv = 1.0 / G[c * D + c];
+        for (int j = 0; j < nrhs; j++) {
+            double a = R[c * ldr + j];
+            for (int l = c + 1; l < D; l++) a -= G[c * D + l] * R[l * ldr + j];
+            R[c * ldr + j] = a * inv;
+        }
+    }
+}
+
+static void irk_gl4_step(int model, const double *x0, const double *u, const double *p, double h, double *xn, double *S) {
+    int nx, nu; model_dims(model, &nx, &nu);
+    const int nc = nx + nu, D = 4 * nx, ldr = S ? nc : 1;
+    double K[4 * NXM], G[16 * NXM * NXM], R[4 * NXM * NSM], xi[NXM], fi[NXM], fx[NXM * NXM], fu[NXM * NUM];
+    memset(K, 0, sizeof(K));
+    for (int it = 0; it < 3 + (S ? 1 : 0); it++) {
+        const int last = it == 3;
+        for (int i = 0; i < 4; i++) {
+            for (int r = 0; r < nx; r++) { double a = 0; for (int j = 0; j < 4; j++) a += GL4_A[i][j] * K[j * nx + r]; xi[r] = x0[r] + h * a; }
+            model_f(model, xi, u, p, fi);
+            model_jac(model, xi, u, p, fx, fu);
+            for (int j = 0; j < 4; j++) {
+                const double ha = h * GL4_A[i][j];
+                for (int r = 0; r < nx; r++) for (int c = 0; c < nx; c++)
+                    G[(i * nx + r) * D + j * nx + c] = ((i == j && r == c) ? 1.0 : 0.0) - ha * fx[r * nx + c];
+            }
+            for (int r = 0; r < nx; r++) {
+                if (!last) R[(i * nx + r) * ldr] = fi[r] - K[i * nx + r];
+                else {
+                    for (int c = 0; c < nx; c++) R[(i * nx + r) * ldr + c] = fx[r * nx + c];
+                    for (int c = 0; c < nu; c++) R[(i * nx + r) * ldr + nx + c] = fu[r * nu + c];
+                }
+            }
+        }
+        lu_solve(D, G, R, ldr, last ? nc : 1);
+        if (!last) for (int e = 0; e < D; e++) K[e] += R[e * ldr];
+    }
+    for (int r = 0; r < nx; r++) { double a = 0; for (int i = 0; i < 4; i++) a += GL4_B[i] * K[i * nx + r]; xn[r] = x0[r] + h * a; }
+    if (S) for (int r = 0; r < nx; r++) for (int c = 0; c < nc; c++) {
+        double a = 0; for (int i = 0; i < 4; i++) a += GL4_B[i] * R[(i * nx + r) * ldr + c];
+        S[r * nc + c] = ((r == c) ? 1.0 : 0.0) + h * a;
+    }
+}
+
 /* ---------------------------------------------------------------------------------------------------------------- */
 /* one solver instance                                                                                              */
 typedef struct {
@@ -170,7 +253,7 @@ static inline double UBX(const orc_opts *o, const inst_t *s, int k, int j) { ret
 
 /* HPIPM residuals of the QP at (z, pi, lam, t); returns mu; norms[4] = inf-norms of res_g, res_b, res_d, res_m */
 static double qp_residuals(const orc_opts *o, inst_t *s, double *norms) {
-    const int nx = s->nx, nu = s->nu, N = s->N;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N;
     double ng = 0, nb = 0, nd = 0, nm = 0, musum = 0; int nc = 0;
     for (int k = 0; k <= N; k++) {
         if (k < N) {
@@ -234,7 +317,7 @@ static inline double rm_of(int mode, double lam, double t, double rd, double dz_
 }
 
 static void kkt_solve(const orc_opts *o, inst_t *s, int fact, int mode, double sigma_mu) {
-    const int nx = s->nx, nu = s->nu, N = s->N;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N;
     double Hu[NUM], Hx[NXM];
     /* modified gradients g~ = res_g + gamma_lb - gamma_ub, and barrier diagonals (kept in P workspace on the fly) */
     /* terminal stage */
@@ -375,7 +458,7 @@ static inline void bound_step(int mode, double lam, double t, double rd, double 
     }
 
 static step_info step_length(const orc_opts *o, inst_t *s, int mode, double sigma_mu) {
-    const int nx = s->nx, nu = s->nu, N = s->N;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N;
     step_info si = {1.0, 0, 0, 0, 0};
     double a_lam = -1.0, a_t = -1.0;   /* HPIPM keeps -alpha */
     FOR_ALL_BOUNDS({
@@ -390,7 +473,7 @@ static step_info step_length(const orc_opts *o, inst_t *s, int mode, double sigm
 }
 
 static void update_vars(const orc_opts *o, inst_t *s, int mode, double sigma_mu, double alpha) {
-    const int nx = s->nx, nu = s->nu, N = s->N;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N;
     const double a = alpha * ((1.0 - alpha) * 0.99 + alpha * 0.9999999);   /* UPDATE_VAR_QP */
     /* lam, t first: they need the old z through rd */
     FOR_ALL_BOUNDS({
@@ -406,7 +489,7 @@ static void update_vars(const orc_opts *o, inst_t *s, int mode, double sigma_mu,
 
 /* HPIPM d_ocp_qp_ipm_solve, cold start.  returns HPIPM status (0 ok, 1 max iter, 2 min step, 3 NaN) */
 static int qp_ipm(const orc_opts *o, inst_t *s, int *iters) {
-    const int nx = s->nx, nu = s->nu, N = s->N;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N;
     memset(s->zu, 0, sizeof(double) * N * nu); memset(s->zx, 0, sizeof(double) * (N + 1) * nx);
     memset(s->ppi, 0, sizeof(double) * (N + 1) * nx);
     memset(s->du_aff, 0, sizeof(double) * N * nu); memset(s->dx_aff, 0, sizeof(double) * (N + 1) * nx);
@@ -462,10 +545,11 @@ static int qp_ipm(const orc_opts *o, inst_t *s, int *iters) {
 }
 
 static void linearise(const orc_opts *o, inst_t *s, const double *p) {
-    const int nx = s->nx, nu = s->nu, N = s->N;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N;
     double S[NXM * NSM], xn[NXM];
     for (int k = 0; k < N; k++) {
-        erk_step(o->model, s->x + k * nx, s->u + k * nu, p, o->dt, o->erk_stages, 1, xn, S);
+        if (o->erk_stages == 0) irk_gl4_step(o->model, s->x + k * nx, s->u + k * nu, p, o->dt, xn, S);
+        else erk_step(o->model, s->x + k * nx, s->u + k * nu, p, o->dt, o->erk_stages, 1, xn, S);
         for (int r = 0; r < nx; r++) {
             for (int c = 0; c < nx; c++) s->A[(k * nx + r) * nx + c] = S[r * (nx + nu) + c];
             for (int c = 0; c < nu; c++) s->B[(k * nx + r) * nu + c] = S[r * (nx + nu) + nx + c];
@@ -476,7 +560,7 @@ static void linearise(const orc_opts *o, inst_t *s, const double *p) {
 
 /* acados ocp_nlp_res_compute; yref = [N][nx+nu] then [nx] */
 static void nlp_residuals(const orc_opts *o, inst_t *s, const double *yref, const double *x0, double *res) {
-    const int nx = s->nx, nu = s->nu, N = s->N, ny = nx + nu;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N, ny = nx + nu;
     double stat = 0, eq = 0, ineq = 0, comp = 0;
     for (int i = 0; i < N * nx; i++) eq = dmax(eq, fabs(s->b[i]));
     for (int j = 0; j < nx; j++) eq = dmax(eq, fabs(x0[j] - s->x[j]));
@@ -506,7 +590,7 @@ static void nlp_residuals(const orc_opts *o, inst_t *s, const double *yref, cons
 
 /* acados SQP; returns acados status (0 ok, 1 failure/NaN input, 2 max iter, 3 min step, 4 QP failure) */
 static int sqp_solve(const orc_opts *o, inst_t *s, const double *x0, const double *yref, const double *p, int *sqp_iter, int *qp_iter) {
-    const int nx = s->nx, nu = s->nu, N = s->N, ny = nx + nu;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N, ny = nx + nu;
     *sqp_iter = 0; *qp_iter = 0;
     for (int j = 0; j < nx; j++) if (!isfinite(x0[j])) return 1;
     for (int i = 0; i < N * ny + nx; i++) if (!isfinite(yref[i])) return 1;
@@ -622,7 +706,7 @@ typedef struct {
 static void solve_one(void *vc, inst_t *s, double *scratch, int i) {
     solve_ctx *c = (solve_ctx *)vc;
     const orc_opts *o = c->o;
-    const int nx = s->nx, nu = s->nu, N = s->N, ny = nx + nu;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N, ny = nx + nu;
     const size_t X = (size_t)(N + 1) * nx, U = (size_t)N * nu;
     (void)scratch;
     memcpy(s->x, c->x + i * X, sizeof(double) * X); memcpy(s->u, c->u + i * U, sizeof(double) * U);
@@ -665,7 +749,7 @@ typedef struct {
 static void closed_loop_one(void *vc, inst_t *s, double *yref, int i) {
     cl_ctx *c = (cl_ctx *)vc;
     const orc_opts *o = c->o;
-    const int nx = s->nx, nu = s->nu, N = s->N, ny = nx + nu, n_steps = c->n_steps, B = c->B;
+    const int nx = ORC_NX(s->nx), nu = ORC_NU(s->nu), N = s->N, ny = nx + nu, n_steps = c->n_steps, B = c->B;
     const double wc[4] = {1e2, 1e2, 1.0, 1.0};
     const double *rt = c->ref + (c->ref_shared ? 0 : (size_t)i * c->rows * 8);
     const double *pc = c->p_ctrl + (size_t)i * 2, *pp = c->p_plant + (size_t)i * 2;

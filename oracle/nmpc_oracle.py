@@ -112,11 +112,61 @@ _ERK = {
 }
 
 
+# Gauss-Legendre collocation with 4 stages (order 8): the tableau of acados sim_irk with its default
+# sim_method_num_stages = 4 (integrator_type 'IRK', reference src/force_model/ocp.py:85).  Nodes = roots of the shifted
+# Legendre polynomial P4, a_ij = int_0^{c_i} l_j, b_j = int_0^1 l_j; computed with 50 digits (mpmath), rounded to double.
+GL4_A = np.array([
+    [0.086963711284363464343, -0.026604180084998793313, 0.012627462689404724515, -0.0035551496857956831569],
+    [0.18811811749986807165, 0.16303628871563653566, -0.027880428602470895224, 0.0067355005945381555154],
+    [0.16719192197418877317, 0.35395300603374396654, 0.16303628871563653566, -0.014190694931141142964],
+    [0.17748257225452261184, 0.3134451147418683468, 0.35267675751627186463, 0.086963711284363464343]])
+GL4_B = np.array([0.17392742256872692869, 0.32607257743127307131, 0.32607257743127307131, 0.17392742256872692869])
+IRK_NEWTON_ITER = 3                 # acados sim_method_newton_iter default
+
+
+def irk_gl4_step(f, jac, x, u, p, T, num_steps=1, sens=True):
+    """acados sim_irk restated (parity unpinned beyond the affine case: acados is not installable here and the reference
+    only integrates the affine force model with it, for which every Newton variant returns the exact discretisation):
+    per step, the stage derivatives K_i solve K_i = f(x + h sum_j a_ij K_j, u); Newton from K = 0 with the exact Jacobian
+    I - h (A (x) f_x) re-evaluated in each of the IRK_NEWTON_ITER iterations, dense LU; the forward sensitivities follow
+    from the implicit function theorem at the final iterate: (I - h A (x) f_x) dK/dw = [f_x S_x, f_x S_u + f_u]."""
+    nx, nu, ns = len(x), len(u), 4
+    h = T / num_steps
+    x = np.array(x, float)
+    S = np.hstack([np.eye(nx), np.zeros((nx, nu))])
+    for _ in range(num_steps):
+        K = np.zeros((ns, nx))
+        for it in range(IRK_NEWTON_ITER + (1 if sens else 0)):
+            last = it == IRK_NEWTON_ITER
+            G = np.eye(ns * nx)
+            R = np.zeros((ns * nx, nx + nu if last else 1))
+            for i in range(ns):
+                xi = x + h * (GL4_A[i] @ K)
+                fx, fu = jac(xi, u, p)
+                for j in range(ns):
+                    G[i * nx:(i + 1) * nx, j * nx:(j + 1) * nx] -= h * GL4_A[i, j] * fx
+                if last:
+                    R[i * nx:(i + 1) * nx] = fx @ S
+                    R[i * nx:(i + 1) * nx, nx:] += fu
+                else:
+                    R[i * nx:(i + 1) * nx, 0] = -(K[i] - f(xi, u, p))
+            sol = np.linalg.solve(G, R)
+            if last:
+                S = S + h * np.tensordot(GL4_B, sol.reshape(ns, nx, nx + nu), axes=1)
+            else:
+                K = K + sol[:, 0].reshape(ns, nx)
+        x = x + h * (GL4_B @ K)
+    return (x, S) if sens else x
+
+
 def erk_step(f, jac, x, u, p, T, num_stages, num_steps=1, sens=True):
     """acados sim_erk: num_steps steps of an explicit RK scheme over [0, T] with forward sensitivities.
+    num_stages = 0 selects the implicit Gauss-Legendre scheme irk_gl4_step instead (the `erk_stages = 0` of the C-ABI).
 
     Returns x_next and, if sens, S = [d x_next/d x, d x_next/d u]  (nx x (nx+nu)).
     """
+    if num_stages == 0:
+        return irk_gl4_step(f, jac, x, u, p, T, num_steps, sens)
     A, b = _ERK[num_stages]
     nx, nu = len(x), len(u)
     h = T / num_steps

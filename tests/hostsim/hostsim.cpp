@@ -17,6 +17,7 @@ using namespace bnmpc;
 
 struct HostGroup {
     static constexpr int L = 1;
+    static constexpr bool PAR_SCAN = false;
     int lane = 0;
     template <class T> T max(T v) const { return v; }
     template <class T> T sum(T v) const { return v; }

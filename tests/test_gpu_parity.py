@@ -497,18 +497,16 @@ def test_results_do_not_depend_on_the_launch_shape(monkeypatch):
 
 
 @pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense'])
-def test_lockstep_and_multi_step_launches_are_bit_identical(model, monkeypatch):
-    """Three schedules of the same closed loop - one warp per instance with a work queue (k_loop_step), the slotted lockstep
-    kernel one launch per step, and the lockstep kernel with many steps per launch (working set resident for a chunk of steps,
-    tickets handed between SMs) - only move work in time: every output is bit-identical, and equal to the oracle's."""
+def test_multi_step_launches_are_bit_identical(model, monkeypatch):
+    """One launch per control step, or many control steps per launch (queue tickets of (instance, chunk of steps): the working
+    set stays on chip inside a chunk, chunks of an instance are handed between SMs) - the schedule only moves work in time:
+    every output is bit-identical for any chunk length / warps per SM / queue order, and equal to the oracle's."""
     B, S = 700, 14
     refs, x0, noise, pc, pp = _fast_loop_inputs(B, S, seed=15, mass_sigma=0.05)
-    monkeypatch.setenv('BNMPC_LOOP_KERNEL', 'warp')
     base, _ = _run_loop(model, refs, x0, noise, pc, pp, S)
-    monkeypatch.setenv('BNMPC_LOOP_KERNEL', 'ls')
     keys = ('Xsim', 'U_ctrl', 'U_plant', 'a', 'cost', 'aed', 'status', 'qp_iter', 'failures')
-    for env, spl in (({}, 1), ({}, S), ({'BNMPC_CHUNK': '3'}, S), ({'BNMPC_CHUNK': '1', 'BNMPC_WARPS_PER_SM': '3'}, 5),
-                     ({'BNMPC_CHUNK': '4', 'BNMPC_NO_ORDER': '1'}, 9)):
+    for env, spl in (({}, S), ({'BNMPC_CHUNK': '3'}, S), ({'BNMPC_CHUNK': '1', 'BNMPC_WARPS_PER_SM': '3'}, 5),
+                     ({'BNMPC_CHUNK': '4', 'BNMPC_NO_ORDER': '1'}, 9), ({'BNMPC_CHUNK': '14', 'BNMPC_WARPS_PER_SM': '1'}, S)):
         for k, v in env.items():
             monkeypatch.setenv(k, v)
         got, _ = _run_loop(model, refs, x0, noise, pc, pp, S, steps_per_launch=spl)
@@ -521,6 +519,31 @@ def test_lockstep_and_multi_step_launches_are_bit_identical(model, monkeypatch):
     want = co.closed_loop(co.default_opts(om), refs[sub], x0[sub], noise[:, sub], pc[sub], pp[sub], S)
     assert np.array_equal(base['status'][sub], want['status']) and np.array_equal(base['qp_iter'][sub], want['qp_iter'])
     np.testing.assert_allclose(base['Xsim'][sub], want['Xsim'], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize('model', ['force', 'jerk', 'force_dense'])
+def test_lockstep_schedule_matches(model, monkeypatch):
+    """The experimental slotted lockstep kernel (BNMPC_LOOP_KERNEL=ls, bnmpc_lockstep.cuh: the warps of a CTA walk the
+    interior-point loop side by side and one warp runs the Riccati sweeps of all of them): bit-identical across its own
+    schedules, same statuses and iteration counts as the default kernel, states within 1e-9 (its sweeps run the stage
+    recurrences as chains, the default kernel as warp-wide scans)."""
+    B, S = 700, 10
+    refs, x0, noise, pc, pp = _fast_loop_inputs(B, S, seed=16, mass_sigma=0.05)
+    base, _ = _run_loop(model, refs, x0, noise, pc, pp, S)
+    monkeypatch.setenv('BNMPC_LOOP_KERNEL', 'ls')
+    first = None
+    for env, spl in (({}, 1), ({}, S), ({'BNMPC_CHUNK': '3', 'BNMPC_LS_GENERATION': '1'}, S), ({'BNMPC_CHUNK': '1', 'BNMPC_WARPS_PER_SM': '3'}, 4)):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got, _ = _run_loop(model, refs, x0, noise, pc, pp, S, steps_per_launch=spl)
+        first = got if first is None else first
+        for k in ('Xsim', 'U_ctrl', 'cost', 'status', 'qp_iter', 'failures'):
+            assert np.array_equal(got[k], first[k]), (env, spl, k)
+        for k in env:
+            monkeypatch.delenv(k)
+    assert np.array_equal(first['status'], base['status']) and np.array_equal(first['qp_iter'], base['qp_iter'])
+    np.testing.assert_allclose(first['Xsim'], base['Xsim'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(first['U_ctrl'], base['U_ctrl'], rtol=0, atol=1e-9)
 
 
 def test_philox_noise_on_device_matches_the_array_path():

@@ -152,3 +152,22 @@ def test_philox_noise_generator():
     a = hs.closed_loop(0, hs.FP64, oo, refs, x0, nz, pc, pp, S, instance_major=True, lockstep=(3, 2))
     b = hs.closed_loop(0, hs.FP64, oo, refs, x0, None, pc, pp, S, instance_major=True, lockstep=(3, 2), philox=(99, 0.01, 12))
     assert np.array_equal(a['Xsim'], b['Xsim']) and np.array_equal(a['U_ctrl'], b['U_ctrl'])
+
+
+@pytest.mark.parametrize('model', [0, hs.MODEL_THRUST])
+def test_irk_integrator_in_the_product_templates(model):
+    """erk_stages = 0: the product's irk_gl4_step (Gauss-Legendre collocation, Newton, IFT sensitivities; acados IRK of
+    reference src/force_model/ocp.py:85) inside linearise / the constant-Jacobian binding, against the C oracle's."""
+    from common import thrust_solve_inputs
+    om = co.MODEL_THRUST if model == hs.MODEL_THRUST else 0
+    x0, yref = thrust_solve_inputs(3, seed=15) if om else random_solve_inputs(0, 3, seed=14)
+    p = np.repeat(np.array([[0.03277, 9.81]]), 3, 0)
+    oo = co.default_opts(om, erk_stages=0)
+    want = co.solve_batch(oo, x0, yref, p)
+    erk = co.solve_batch(co.default_opts(om), x0, yref, p)
+    got = hs.solve_batch(model, hs.FP64, hs.opts_from_oracle(oo), x0, yref, p)
+    for ref in (want, erk):
+        assert np.array_equal(got['status'], ref['status']) and np.array_equal(got['sqp_iter'], ref['sqp_iter'])
+        assert np.array_equal(got['qp_iter'], ref['qp_iter'])
+        np.testing.assert_allclose(got['u'], ref['u'], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(got['x'], ref['x'], rtol=0, atol=1e-10)

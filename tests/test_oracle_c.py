@@ -94,3 +94,52 @@ def test_c_vs_numpy_nonlinear_thrust_ocp():
         assert sol.sqp_iter == rc['sqp_iter'][i] and sol.qp_iter == rc['qp_iter'][i]
         np.testing.assert_allclose(rc['u'][i], sol.u, rtol=0, atol=1e-9)
         np.testing.assert_allclose(rc['x'][i], sol.x, rtol=0, atol=1e-9)
+
+
+def test_irk_gl4_integrator():
+    """erk_stages = 0 = acados IRK (Gauss-Legendre, 4 stages, 3 Newton iterations, IFT sensitivities), the integrator_type
+    of the reference's force OCP (src/force_model/ocp.py:85).  (a) On the affine force model and on the plant (linear in
+    the state for a constant input) it returns the exact discretisation = ERK4, state and sensitivities, to 1e-14.  (b) On
+    a system that is nonlinear in the state it agrees with a tight-tolerance scipy solve_ivp to 1e-9 and its sensitivities
+    with finite differences.  (c) The OCP solved with it (C oracle, numpy oracle) equals the ERK4 solution to 1e-12 with
+    identical iteration counts."""
+    from scipy.integrate import solve_ivp
+    from common import P_NOM, random_solve_inputs, thrust_solve_inputs
+    rng = np.random.default_rng(4)
+    p = (o.MASS, o.GRAVITY_ACC)
+    for f, jac, u in ((o.f_force, o.jac_force, np.array([0.1, 0.3])), (o.f_plant, o.jac_plant, np.array([0.4, 0.35]))):
+        x = rng.normal(size=4)
+        xe, Se = o.erk_step(f, jac, x, u, p, 0.02, 4)
+        xi, Si = o.erk_step(f, jac, x, u, p, 0.02, 0)
+        assert np.abs(xe - xi).max() < 1e-14 and np.abs(Se - Si).max() < 1e-14
+        sol = solve_ivp(lambda t, y: f(y, u, p), [0, 0.02], x, rtol=1e-13, atol=1e-14)
+        assert np.abs(sol.y[:, -1] - xi).max() < 1e-12
+    f = lambda x, u, p: np.array([x[1], -9.0 * np.sin(x[0]) + u[0]])                     # pendulum: Newton has work to do
+    jac = lambda x, u, p: (np.array([[0, 1.0], [-9.0 * np.cos(x[0]), 0]]), np.array([[0.0], [1.0]]))
+    x, u = np.array([1.0, 0.5]), np.array([0.3])
+    xi, Si = o.erk_step(f, jac, x, u, p, 0.1, 0)
+    sol = solve_ivp(lambda t, y: f(y, u, p), [0, 0.1], x, rtol=1e-13, atol=1e-14)
+    assert np.abs(sol.y[:, -1] - xi).max() < 1e-9
+    eps, fd = 1e-6, np.zeros((2, 3))
+    for j in range(3):
+        dx, du = np.zeros(2), np.zeros(1)
+        (dx if j < 2 else du)[j if j < 2 else 0] = eps
+        fd[:, j] = (o.erk_step(f, jac, x + dx, u + du, p, 0.1, 0, sens=False) - o.erk_step(f, jac, x - dx, u - du, p, 0.1, 0, sens=False)) / (2 * eps)
+    assert np.abs(fd - Si).max() < 1e-8
+    for model, gen in ((co.MODEL_FORCE, lambda: random_solve_inputs(0, 5, seed=3)), (co.MODEL_THRUST, lambda: thrust_solve_inputs(5, seed=4))):
+        x0, yref = gen()
+        pb = np.repeat(P_NOM[None], 5, 0)
+        a = co.solve_batch(co.default_opts(model), x0, yref, pb)
+        b = co.solve_batch(co.default_opts(model, erk_stages=0), x0, yref, pb)
+        assert np.array_equal(a['qp_iter'], b['qp_iter']) and np.array_equal(a['sqp_iter'], b['sqp_iter']) and np.array_equal(a['status'], b['status'])
+        np.testing.assert_allclose(a['u'], b['u'], rtol=0, atol=1e-12)
+    spec = o.force_ocp(); spec.erk_stages = 0
+    s_irk, s_erk = o.OracleOcpSolver(spec), o.OracleOcpSolver(o.force_ocp())
+    x0, yref = random_solve_inputs(0, 1, seed=5)
+    for s in (s_irk, s_erk):
+        for k in range(30):
+            s.set(k, 'yref', yref[0, k * 6:(k + 1) * 6])
+        s.set(30, 'yref', yref[0, 180:])
+        s.set(0, 'lbx', x0[0]); s.set(0, 'ubx', x0[0])
+        assert s.solve() == 0
+    np.testing.assert_allclose(s_irk.get(0, 'u'), s_erk.get(0, 'u'), rtol=0, atol=1e-12)
