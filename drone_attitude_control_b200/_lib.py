@@ -11,7 +11,7 @@ MODELS = {'force': MODEL_FORCE, 'jerk': MODEL_JERK, 'force_dense': MODEL_FORCE_D
 FP64, FP32 = 0, 1
 # acados return values (reference src/Readme.md:14-20)
 SUCCESS, FAILURE, MAXITER, MINSTEP, QP_FAILURE = 0, 1, 2, 3, 4
-FIELDS = {'x': 0, 'u': 1, 'yref': 2, 'lbx': 3, 'ubx': 4, 'p': 5, 'pi': 6, 'lam': 7}
+FIELDS = {'x': 0, 'u': 1, 'yref': 2, 'lbx': 3, 'ubx': 4, 'p': 5, 'pi': 6, 'lam': 7, 'lbu': 8, 'ubu': 9}
 STATS = {'status': 0, 'sqp_iter': 1, 'qp_iter': 2}
 
 

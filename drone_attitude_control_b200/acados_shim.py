@@ -75,7 +75,8 @@ class BatchedAcadosOcpSolver:
         N = self.N
         return {'x': self.nx if 0 <= stage <= N else 0, 'u': self.nu if 0 <= stage < N else 0,
                 'yref': (self.ny if 0 <= stage < N else (self.ny_e if stage == N else 0)),
-                'lbx': self.nx if stage == 0 else 0, 'ubx': self.nx if stage == 0 else 0, 'p': self.np_,
+                'lbx': self.nx if 0 <= stage < N else 0, 'ubx': self.nx if 0 <= stage < N else 0, 'p': self.np_,
+                'lbu': self.nu if 0 <= stage < N else 0, 'ubu': self.nu if 0 <= stage < N else 0,
                 'pi': self.nx if 0 <= stage < N else 0,
                 'lam': 2 * self.nu if stage == 0 else (2 * (self.nu + self.nx) if 0 < stage < N else 0)}[field]
 

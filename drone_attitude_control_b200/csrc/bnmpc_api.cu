@@ -122,6 +122,24 @@ __global__ void k_field(const __grid_constant__ Gs<T> gs, int NX, int NU, int NP
     if (TO_STATE) *p = T(aos[(size_t)inst * aos_stride + j]); else aos[(size_t)inst * aos_stride + j] = double(*p);
 }
 
+// per-stage bounds [B][N][2][NU+NX]: fill with the configuration's boxes / copy one (stage, side, u|x) slice to or from AoS
+__global__ void k_bnd_init(int B, int N, int NX, int NU, const __grid_constant__ Opts o, double* bnd) {
+    const int SG = NU + NX;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * N * 2 * SG) return;
+    const int j = (int)(idx % SG), side = (int)((idx / SG) % 2);
+    bnd[idx] = j < NU ? (side ? o.ubu[j] : o.lbu[j]) : (side ? o.ubx[j - NU] : o.lbx[j - NU]);
+}
+template <bool TO_STATE>
+__global__ void k_bnd_field(int B, int N, int NX, int NU, int stage, int side, int is_x, double* bnd, double* aos) {
+    const int SG = NU + NX, dim = is_x ? NX : NU;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * dim) return;
+    const int inst = (int)(idx / dim), j = (int)(idx % dim);
+    double* p = bnd + (((size_t)inst * N + stage) * 2 + side) * SG + (is_x ? NU : 0) + j;
+    if (TO_STATE) *p = aos[idx]; else aos[idx] = *p;
+}
+
 // OCP.set_up_ocp in one call: [B][N*ny + ny_e]
 template <class T>
 __global__ void k_yref_all(const __grid_constant__ Gs<T> gs, int NX, int NU, int NP, const double* aos) {
@@ -332,6 +350,29 @@ int refresh_order(Handle* h) {
     return 0;
 }
 
+// 'lbu' / 'ubu' at any stage and 'lbx' / 'ubx' at stages >= 1 live in per-instance storage that exists only once such a
+// field has been set (until then every stage uses the boxes of the configuration and the solve kernels carry no lookup)
+bool is_stage_bound(int field, int stage) {
+    return field == F_LBU || field == F_UBU || ((field == F_LBX || field == F_UBX) && stage >= 1);
+}
+int ensure_bounds(Handle* h) {
+    if (h->gs.BND) return 0;
+    const size_t tot = (size_t)h->batch * h->cfg.horizon * 2 * (h->ops->nu + h->ops->nx);
+    CK(cudaMalloc(&h->gs.BND, tot * sizeof(double)));
+    k_bnd_init<<<(unsigned)((tot + 255) / 256), 256, 0, h->stream>>>(h->batch, h->cfg.horizon, h->ops->nx, h->ops->nu, h->opts, h->gs.BND);
+    CK(cudaGetLastError()); h->launches++;
+    return 0;
+}
+int bound_xfer(Handle* h, int field, int stage, double* aos, int to_state) {
+    const int is_x = (field == F_LBX || field == F_UBX), side = (field == F_UBX || field == F_UBU);
+    const size_t tot = (size_t)h->batch * (is_x ? h->ops->nx : h->ops->nu);
+    const unsigned grid = (unsigned)((tot + 127) / 128);
+    if (to_state) k_bnd_field<true><<<grid, 128, 0, h->stream>>>(h->batch, h->cfg.horizon, h->ops->nx, h->ops->nu, stage, side, is_x, h->gs.BND, aos);
+    else k_bnd_field<false><<<grid, 128, 0, h->stream>>>(h->batch, h->cfg.horizon, h->ops->nx, h->ops->nu, stage, side, is_x, h->gs.BND, aos);
+    CK(cudaGetLastError()); h->launches++;
+    return 0;
+}
+
 int reset_iterate(Handle* h) {
     const size_t es = h->ops->elem_size, B = h->batch;
     CK(cudaMemsetAsync(h->gs.V, 0, B * h->nV * es, h->stream));
@@ -497,6 +538,7 @@ int bnmpc_destroy(void* handle) {
     if (h->next_step) cudaFree(h->next_step);
     if (h->xs) cudaFree(h->xs);
     if (h->gs.U0) cudaFree(h->gs.U0);
+    if (h->gs.BND) cudaFree(h->gs.BND);
     for (int i = 0; i < 4; i++) if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -537,13 +579,17 @@ int64_t bnmpc_workspace_bytes(void* handle) {
 int bnmpc_set(void* handle, int stage, int field, const double* value, int on_device) {
     Handle* h = (Handle*)handle;
     if (!h || !value) return fail(BNMPC_E_ARG, "NULL argument");
-    if (field < BNMPC_F_X || field > BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "unknown field");
+    if (field < BNMPC_F_X || field > BNMPC_F_UBU) return fail(BNMPC_E_FIELD, "unknown field");
     if (field == BNMPC_F_PI || field == BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "field is read-only");
     const int dim = field_dim(h->ops->nx, h->ops->nu, h->ops->np, field, stage, h->cfg.horizon);
     if (dim <= 0) return fail(BNMPC_E_STAGE, "field does not exist at this stage");
     if (use_device(h)) return BNMPC_E_CUDA;
     const double* d;
     if (int rc = stage_in(h, 0, value, (size_t)h->batch * dim, on_device, &d)) return rc;
+    if (is_stage_bound(field, stage)) {
+        if (int rc = ensure_bounds(h)) return rc;
+        return bound_xfer(h, field, stage, const_cast<double*>(d), 1);
+    }
     CK(field_xfer(h, field, stage, const_cast<double*>(d), dim, dim, 1));
     return 0;
 }
@@ -551,12 +597,17 @@ int bnmpc_set(void* handle, int stage, int field, const double* value, int on_de
 int bnmpc_get(void* handle, int stage, int field, double* out, int on_device) {
     Handle* h = (Handle*)handle;
     if (!h || !out) return fail(BNMPC_E_ARG, "NULL argument");
-    if (field < BNMPC_F_X || field > BNMPC_F_LAM) return fail(BNMPC_E_FIELD, "unknown field");
+    if (field < BNMPC_F_X || field > BNMPC_F_UBU) return fail(BNMPC_E_FIELD, "unknown field");
     const int dim = field_dim(h->ops->nx, h->ops->nu, h->ops->np, field, stage, h->cfg.horizon);
     if (dim <= 0) return fail(BNMPC_E_STAGE, "field does not exist at this stage");
     if (use_device(h)) return BNMPC_E_CUDA;
     double* d;
     if (int rc = stage_out_begin(h, 1, out, (size_t)h->batch * dim, on_device, &d)) return rc;
+    if (is_stage_bound(field, stage)) {          // (reading a bound materialises the storage: it then holds the configuration's boxes)
+        if (int rc = ensure_bounds(h)) return rc;
+        if (int rc = bound_xfer(h, field, stage, d, 0)) return rc;
+        return stage_out_end(h, 1, out, (size_t)h->batch * dim, on_device);
+    }
     CK(field_xfer(h, field, stage, d, dim, dim, 0));
     return stage_out_end(h, 1, out, (size_t)h->batch * dim, on_device);
 }
@@ -596,7 +647,7 @@ int bnmpc_solve(void* handle) {
     if (int rc = refresh_order(h)) return rc;
     int* q;
     if (int rc = next_queue(h, &q)) return rc;
-    CK(h->ops->solve(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
+    CK((h->gs.BND ? h->ops->solve_sb : h->ops->solve)(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
     return 0;
 }
 
@@ -618,7 +669,7 @@ int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* stat
     if (int rc = refresh_order(h)) return rc;
     int* q;
     if (int rc = next_queue(h, &q)) return rc;
-    CK(h->ops->solve(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
+    CK((h->gs.BND ? h->ops->solve_sb : h->ops->solve)(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
     if (u0) CK(cudaMemcpyAsync(u0, h->gs.U0, sizeof(double) * B * nu, out, h->stream));   // gathered by the solve kernel
     if (status) CK(cudaMemcpyAsync(status, h->gs.status, sizeof(int32_t) * B, out, h->stream));
     if (!on_device) CK(cudaStreamSynchronize(h->stream));
@@ -700,6 +751,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     if (a->n_steps < 0 || a->first_step < 0) return fail(BNMPC_E_ARG, "negative step count");
     if (a->first_step + a->n_steps + h->cfg.horizon > a->ref_rows) return fail(BNMPC_E_ARG, "ref has too few rows for first_step + n_steps + N");
     if (a->noise_philox && a->noise) return fail(BNMPC_E_ARG, "noise array and noise_philox are exclusive");
+    if (h->gs.BND) return fail(BNMPC_E_UNSUPPORTED, "per-stage bounds ('lbu'/'ubu', 'lbx'/'ubx' at stages >= 1) belong to the solve() path; the fused closed loop uses the boxes of the configuration, like the reference's follow_trajectory");
     const bool logs = a->noise || a->Xsim || a->U_plant || a->U_ctrl || a->a_log || a->status || a->qp_iter;
     if (logs && a->log_stride < a->first_step + a->n_steps) return fail(BNMPC_E_ARG, "log_stride too small");
     if (use_device(h)) return BNMPC_E_CUDA;

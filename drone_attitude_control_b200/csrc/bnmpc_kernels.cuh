@@ -40,6 +40,7 @@ struct GsAny {
     void *V, *PI, *LAM, *YREF, *X0, *PAR;
     int32_t *status, *sqp_iter, *qp_iter, *have_mult;
     double* U0;
+    double* BND;
     int B, N;
 };
 template <class T> inline Gs<T> gs_cast(const GsAny& a) {
@@ -53,6 +54,9 @@ struct ModelOps {
     size_t (*smem_bytes)(int N);                                    // dynamic shared memory of one instance (one warp)
     int (*tmem_cols)(int N, int warps);                             // tensor-memory columns a CTA of `warps` allocates (0 = too many)
     cudaError_t (*solve)(const GsAny&, const Opts&, int ctas, int warps, int* queue, cudaStream_t);
+    // the same for handles whose instances carry per-stage bounds (GsAny::BND): a second instantiation of the solve kernel, so
+    // that the lookup costs the common case nothing
+    cudaError_t (*solve_sb)(const GsAny&, const Opts&, int ctas, int warps, int* queue, cudaStream_t);
     cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
     // slotted lockstep schedule (bnmpc_lockstep.cuh): LoopArgs::n_steps control steps per launch, tickets of LoopArgs::chunk steps
     cudaError_t (*loop_ls)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
@@ -91,9 +95,10 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ double words_to(uint32_t lo, uint32_t hi, double) { return __hiloint2double((int)hi, (int)lo); }
 __device__ __forceinline__ float words_to(uint32_t lo, uint32_t, float) { return __uint_as_float(lo); }
 
-template <class M, class T>
+template <class M, class T, bool SB = false>
 struct TmemPriv {
     static constexpr bool IN_SMEM = false;
+    static constexpr bool STAGE_BOUNDS = SB;                        // per-stage bounds looked up per item (API solve kernel only)
     static constexpr int s = M::NXB + M::NUB, n = M::NXB;
     static constexpr int WPE = (int)sizeof(T) / 4;                 // 32-bit words per element
     static constexpr bool TI_PRIV = true;                          // the reciprocals 1/t travel with the record (7 s elements)
@@ -260,13 +265,13 @@ struct DevTickets {
     }
 };
 
-template <class M, class T>
+template <class M, class T, bool SB>
 __global__ void __launch_bounds__(32 * LaunchShape<M, T>::MAX_WARPS, 1)
 k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, int* queue, int tmem_cols) {
     const uint32_t tbase = tmem_alloc_cta(tmem_cols);
     const WarpGroup<32> g;
-    const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
-    Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
+    const TmemPriv<M, T, SB> ps{TmemPriv<M, T, SB>::warp_base(tbase, o.N)};
+    Solver<M, T, WarpGroup<32>, TmemPriv<M, T, SB>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
     for (int inst = next_instance(queue, o.order, gs.B); inst < gs.B; inst = next_instance(queue, o.order, gs.B)) api_solve<M, T>(sv, inst, gs);
     tmem_free_cta(tbase, tmem_cols);
 }
@@ -409,7 +414,9 @@ struct OpsImpl {
         if (e != cudaSuccess) return e;
         e = prep(k_loop_ls<M, T>, 0);
         if (e != cudaSuccess) return e;
-        e = prep(k_solve<M, T>, 0);
+        e = prep(k_solve<M, T, false>, 0);
+        if (e != cudaSuccess) return e;
+        e = prep(k_solve<M, T, true>, 0);
         if (e != cudaSuccess) return e;
         int dev = 0, optin = 0;
         e = cudaGetDevice(&dev);
@@ -426,7 +433,13 @@ struct OpsImpl {
     static cudaError_t solve(const GsAny& a, const Opts& o_, int ctas, int warps, int* queue, cudaStream_t st) {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
-        k_solve<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps));
+        k_solve<M, T, false><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps));
+        return cudaGetLastError();
+    }
+    static cudaError_t solve_sb(const GsAny& a, const Opts& o_, int ctas, int warps, int* queue, cudaStream_t st) {
+        Opts o = o_;
+        o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
+        k_solve<M, T, true><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps));
         return cudaGetLastError();
     }
     static cudaError_t loop_step(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int* queue, cudaStream_t st) {
@@ -443,7 +456,7 @@ struct OpsImpl {
     }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, &smem_bytes, &tmem_cols, &solve, &loop_step, &loop_ls, &cta_shape};
+                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, &smem_bytes, &tmem_cols, &solve, &solve_sb, &loop_step, &loop_ls, &cta_shape};
     }
 };
 

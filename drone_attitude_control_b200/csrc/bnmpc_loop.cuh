@@ -10,7 +10,7 @@
 namespace bnmpc {
 
 // field ids of the C-ABI (include/bnmpc.h)
-enum { F_X = 0, F_U = 1, F_YREF = 2, F_LBX = 3, F_UBX = 4, F_P = 5, F_PI = 6, F_LAM = 7 };
+enum { F_X = 0, F_U = 1, F_YREF = 2, F_LBX = 3, F_UBX = 4, F_P = 5, F_PI = 6, F_LAM = 7, F_LBU = 8, F_UBU = 9 };
 enum { KIND_FORCE = 0, KIND_JERK = 1, KIND_THRUST = 2 };
 enum { REF_BATCH_MINOR = 0, REF_SHARED = 1, REF_INSTANCE_MAJOR = 2, REF_CIRCLE = 3 };   // bnmpc_closed_loop_args.ref_shared
 
@@ -26,7 +26,8 @@ BN_HD int field_dim(int NX, int NU, int NP, int field, int stage, int N) {
     case F_X: return (stage >= 0 && stage <= N) ? NX : 0;
     case F_U: return (stage >= 0 && stage < N) ? NU : 0;
     case F_YREF: return (stage >= 0 && stage < N) ? NX + NU : (stage == N ? NX : 0);
-    case F_LBX: case F_UBX: return stage == 0 ? NX : 0;
+    case F_LBX: case F_UBX: return (stage >= 0 && stage < N) ? NX : 0;      // stage 0: the x0 embedding; 1..N-1: state box
+    case F_LBU: case F_UBU: return (stage >= 0 && stage < N) ? NU : 0;
     case F_P: return NP;
     case F_PI: return (stage >= 0 && stage < N) ? NX : 0;
     case F_LAM: return (stage == 0) ? 2 * NU : ((stage > 0 && stage < N) ? 2 * (NU + NX) : 0);
@@ -260,6 +261,7 @@ BN_HD void api_solve(Solver<M, T, G, PS>& sv, int inst, const Gs<T>& gs) {
         for (int j = 0; j < NP; j++) p[j] = gs.PAR[(size_t)inst * NP + j];
         sv.set_par(p);
         for (int gi = sv.g.lane; gi < NX; gi += G::L) sv.X0S(gi) = gs.X0[(size_t)inst * NX + gi];
+        sv.bnd = gs.BND ? gs.BND + (size_t)inst * gs.N * 2 * (NU + NX) : nullptr;
     }
     sv.g.sync();
     sv.template sqp_solve<T>(inst, gs, ys);

@@ -35,7 +35,11 @@ class OCP:
         self.integrator = None
         self._batch, self._device, self._precision, self._overrides = batch, device, precision, solver_overrides
 
-    def create_ocp(self, model=None):
+    def create_ocp(self, model=None, **ocp_overrides):
+        """The OCP of the reference's create_ocp; `ocp_overrides` replace its numbers (fields of bnmpc_config: W, W_e, lbx, ubx,
+        lbu, ubu, horizon, dt, tol, ...), e.g. create_ocp(ubu=[0.3, 0.4]).  `model` is accepted for signature compatibility:
+        the dynamics are the generated device code of MODEL."""
+        self._overrides.update(ocp_overrides)
         # LINEAR_LS cost, W = blkdiag(diag(100,100,1,1), diag(.1,.1)), W_e, Vx/Vu selection, BGH boxes on u and x, x0 = 0
         self.ocp = dict(model=self.MODEL)
 
@@ -60,3 +64,28 @@ class OCP:
         for k in range(p.N_horizon):
             self.ocp_solver.set(k, 'yref', np.hstack((xref[iter + k], uref[iter + k])))
         self.ocp_solver.set(p.N_horizon, 'yref', xref[iter + p.N_horizon])
+
+
+def follow_trajectory(xref, uref, x0, noise, verbose=False, device=0):
+    """follow_trajectory of the reference (src/force_model/controller.py:8-56) - same arguments, same return value (closedLoopCost, Xsim
+    [N+1, 4], a [N, 2], U_opt_plant [N, 2]) - run as ONE drone of the fused device-resident loop (BatchedClosedLoop): per
+    control step one kernel does set_up_ocp, the x0 embedding, solve(), Converter.convert, simulate_next_x and the logged cost.
+    `noise` draws np.random.normal(0, p.noise) once per control step from numpy's global stream, in the reference's order.
+    A non-zero solver status raises, as the reference does."""
+    import torch
+    from ..closed_loop import BatchedClosedLoop
+    ref = np.zeros((xref.shape[0], 8))
+    ref[:, :4] = xref[:, :4]
+    ref[:, 4:4 + uref.shape[1]] = uref
+    eps = np.array([np.random.normal(0, p.noise) if noise else 0.0 for _ in range(p.N)])
+    loop = BatchedClosedLoop(OCP.MODEL, batch=1, device=device)
+    loop.init(torch.tensor(np.asarray(x0, float)[:, None]), torch.tensor(ref), noise=torch.tensor(eps[:, None]), n_steps=p.N)
+    loop.run(steps_per_launch=p.N)
+    r = loop.results()
+    status = r['status'][0].cpu().numpy()
+    if status.any():
+        k = int(np.flatnonzero(status)[0])
+        raise Exception(f'Failed in iteration {k}\nbnmpc ocp_solver returned status {status[k]}')
+    if verbose:
+        loop.solver.print_statistics()
+    return float(r['cost'][0]), r['Xsim'][0].cpu().numpy(), r['a'][0].cpu().numpy(), r['U_plant'][0].cpu().numpy()

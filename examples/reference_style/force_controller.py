@@ -1,10 +1,18 @@
+# examples/reference_style - NOT part of the bnmpc package.
+#
+# This file transcribes the reference's own host loop (BroilerCompiler/drone-attitude-control, GPL-3.0, src/force_model/controller.py:8-56) with
+# the acados constructors swapped for the bnmpc shims, to show that the shims are a drop-in for that loop (same names, same
+# call order, batch = 1, numpy in / out) and to reproduce the reference's committed run step by step
+# (tests/test_gpu_parity.py::test_reference_style_main_reproduces_reference_run).  The product's own entry points for this
+# path are drone_attitude_control_b200.force_model / jerk_model.follow_trajectory (fused, device-resident) and
+# BatchedClosedLoop.
 """follow_trajectory of the force model, written like reference src/force_model/controller.py:8-56 (same loop, same
 calls) against the libbnmpc shims.  This is the step-by-step host path (one set/solve/get round trip per call); the
 fused device-resident loop for many drones is drone_attitude_control_b200.closed_loop.BatchedClosedLoop."""
 import numpy as np
 
-from ..params import DroneData, ExperimentParameters
-from .ocp import OCP, Converter
+from drone_attitude_control_b200.params import DroneData, ExperimentParameters
+from drone_attitude_control_b200.force_model.ocp import OCP, Converter
 
 
 def follow_trajectory(xref, uref, x0, noise, verbose=True, device=0):

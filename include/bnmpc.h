@@ -59,11 +59,19 @@ extern "C" {
 #define BNMPC_F_X 0      /* 'x'    stage 0..N,   dim nx   (get/set) */
 #define BNMPC_F_U 1      /* 'u'    stage 0..N-1, dim nu   (get/set) */
 #define BNMPC_F_YREF 2   /* 'yref' stage 0..N-1 dim nx+nu, stage N dim nx (set/get) */
-#define BNMPC_F_LBX 3    /* 'lbx'  stage 0 only: x0 embedding (controller.py:30) */
-#define BNMPC_F_UBX 4    /* 'ubx'  stage 0 only: x0 embedding (controller.py:31); must equal lbx */
+#define BNMPC_F_LBX 3    /* 'lbx'  stage 0: x0 embedding (controller.py:30); stages 1..N-1: lower state bound of that stage */
+#define BNMPC_F_UBX 4    /* 'ubx'  stage 0: x0 embedding (controller.py:31), must equal lbx; stages 1..N-1: upper state bound */
 #define BNMPC_F_P 5      /* 'p'    stage ignored, dim 2 = (mass, g) of the controller model (north-star extension) */
 #define BNMPC_F_PI 6     /* 'pi'   stage 0..N-1, dim nx   (get) */
 #define BNMPC_F_LAM 7    /* 'lam'  stage 0..N-1, dim 2*(nu[+nx]) = [lbu, lbx, ubu, ubx] multipliers (get) */
+#define BNMPC_F_LBU 8    /* 'lbu'  stage 0..N-1, dim nu: lower input bound of that stage (get/set) */
+#define BNMPC_F_UBU 9    /* 'ubu'  stage 0..N-1, dim nu: upper input bound of that stage (get/set) */
+/* Per-stage bounds ('lbu'/'ubu', and 'lbx'/'ubx' at stages >= 1): acados' ocp_solver.set accepts them at any stage; the
+ * reference fixes its boxes once in create_ocp (src/force_model/ocp.py:62-76) and never sets them per stage.  Until the first
+ * such set() every stage of every instance uses the boxes of bnmpc_config (lbu/ubu/lbx/ubx) and no kernel looks anything
+ * up; the first set() allocates per-instance storage ([batch][N][2][nu+nx] doubles, initialised with those boxes) and
+ * bnmpc_solve / bnmpc_solve_for_x0 switch to a second instantiation of the solve kernel that reads the bounds per stage.
+ * bnmpc_closed_loop_run refuses (BNMPC_E_UNSUPPORTED) on such a handle. */
 
 /* per-instance int32 statistics: reference `ocp_solver.get_stats(name)` */
 #define BNMPC_STAT_STATUS 0

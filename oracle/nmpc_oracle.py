@@ -427,6 +427,10 @@ class OracleOcpSolver:
         self.yref = np.zeros((s.N, s.nx + s.nu))
         self.yref_e = np.zeros(s.nx)
         self.x0 = np.zeros(s.nx)
+        # per-stage boxes (acados accepts 'lbu' / 'ubu' at every stage and 'lbx' / 'ubx' at stages 1..N-1 through set();
+        # the reference leaves them at the values of create_ocp, src/force_model/ocp.py:62-76)
+        self.lbu_k = np.tile(s.lbu, (s.N, 1)); self.ubu_k = np.tile(s.ubu, (s.N, 1))
+        self.lbx_k = np.tile(s.lbx, (s.N, 1)); self.ubx_k = np.tile(s.ubx, (s.N, 1))
         self.lam = None
         self.status = 0
         self.sqp_iter = 0
@@ -451,10 +455,12 @@ class OracleOcpSolver:
                 self.yref_e[:] = val
             else:
                 self.yref[stage] = val
-        elif fld in ('lbx', 'ubx'):
+        elif fld in ('lbx', 'ubx') and stage == 0:
             # the reference only sets stage 0 (x0 embedding, controller.py:30-31)
-            assert stage == 0
             self.x0[:] = val
+        elif fld in ('lbx', 'ubx', 'lbu', 'ubu'):
+            assert (1 if fld.endswith('x') else 0) <= stage < s.N
+            getattr(self, fld + '_k')[stage] = val
         elif fld == 'x':
             self.x[stage] = val
         elif fld == 'u':
@@ -494,14 +500,14 @@ class OracleOcpSolver:
             ou = self.off_u[k]
             Hd[ou:ou + s.nu] = s.dt * s.w[s.nx:]
             q[ou:ou + s.nu] = s.dt * s.w[s.nx:] * (self.u[k] - self.yref[k, s.nx:])
-            lb[ou:ou + s.nu] = s.lbu - self.u[k]
-            ub[ou:ou + s.nu] = s.ubu - self.u[k]
+            lb[ou:ou + s.nu] = self.lbu_k[k] - self.u[k]
+            ub[ou:ou + s.nu] = self.ubu_k[k] - self.u[k]
             if k >= 1:
                 ox = self.off_x[k]
                 Hd[ox:ox + s.nx] = s.dt * s.w[:s.nx]
                 q[ox:ox + s.nx] = s.dt * s.w[:s.nx] * (self.x[k] - self.yref[k, :s.nx])
-                lb[ox:ox + s.nx] = s.lbx - self.x[k]
-                ub[ox:ox + s.nx] = s.ubx - self.x[k]
+                lb[ox:ox + s.nx] = self.lbx_k[k] - self.x[k]
+                ub[ox:ox + s.nx] = self.ubx_k[k] - self.x[k]
             rows = slice(k * s.nx, (k + 1) * s.nx)
             G[rows, ou:ou + s.nu] = B[k]
             if k >= 1:
@@ -531,7 +537,7 @@ class OracleOcpSolver:
                 gu = s.dt * s.w[s.nx:] * (self.u[k] - self.yref[k, s.nx:]) + B[k].T @ self.pi[k] \
                     - lam_lb[ou:ou + s.nu] + lam_ub[ou:ou + s.nu]
                 stat = max(stat, np.max(np.abs(gu)))
-                for lo, hi, v, ll, lu in ((s.lbu, s.ubu, self.u[k], lam_lb[ou:ou + s.nu], lam_ub[ou:ou + s.nu]),):
+                for lo, hi, v, ll, lu in ((self.lbu_k[k], self.ubu_k[k], self.u[k], lam_lb[ou:ou + s.nu], lam_ub[ou:ou + s.nu]),):
                     ineq = max(ineq, np.max(np.maximum(lo - v, 0)), np.max(np.maximum(v - hi, 0)))
                     comp = max(comp, np.max(np.abs(ll * (lo - v))), np.max(np.abs(lu * (v - hi))))
             if k >= 1:
@@ -540,9 +546,9 @@ class OracleOcpSolver:
                     gx = s.dt * s.w[:s.nx] * (self.x[k] - self.yref[k, :s.nx]) + A[k].T @ self.pi[k] - self.pi[k - 1] \
                         - lam_lb[ox:ox + s.nx] + lam_ub[ox:ox + s.nx]
                     v = self.x[k]
-                    ineq = max(ineq, np.max(np.maximum(s.lbx - v, 0)), np.max(np.maximum(v - s.ubx, 0)))
-                    comp = max(comp, np.max(np.abs(lam_lb[ox:ox + s.nx] * (s.lbx - v))),
-                               np.max(np.abs(lam_ub[ox:ox + s.nx] * (v - s.ubx))))
+                    ineq = max(ineq, np.max(np.maximum(self.lbx_k[k] - v, 0)), np.max(np.maximum(v - self.ubx_k[k], 0)))
+                    comp = max(comp, np.max(np.abs(lam_lb[ox:ox + s.nx] * (self.lbx_k[k] - v))),
+                               np.max(np.abs(lam_ub[ox:ox + s.nx] * (v - self.ubx_k[k]))))
                 else:
                     gx = s.w_e * (self.x[k] - self.yref_e) - self.pi[k - 1]
                 stat = max(stat, np.max(np.abs(gx)))

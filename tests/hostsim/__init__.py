@@ -69,7 +69,8 @@ def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int)) if a is not None else None
 
 
-def solve_batch(model, prec, o, x0, yref, p, x=None, u=None):
+def solve_batch(model, prec, o, x0, yref, p, x=None, u=None, bnd=None):
+    """bnd: per-stage bounds [B, N, 2, nu + nx] (lower / upper, per stage [u; x]) or None = the boxes of `o`"""
     nx = 6 if model in (1, 3) else 4
     B, N = x0.shape[0], o.N
     x0 = np.ascontiguousarray(x0, float); yref = np.ascontiguousarray(yref, float); p = np.ascontiguousarray(p, float)
@@ -77,7 +78,9 @@ def solve_batch(model, prec, o, x0, yref, p, x=None, u=None):
     u = np.zeros((B, N, 2)) if u is None else np.array(u, float, order='C')
     pi = np.zeros((B, N, nx))
     st = np.zeros(B, np.int32); si = np.zeros(B, np.int32); qi = np.zeros(B, np.int32)
-    rc = lib().hs_solve_batch(model, prec, C.byref(o), B, _dp(x0), _dp(yref), _dp(p), _dp(x), _dp(u), _dp(pi), _ip(st), _ip(si), _ip(qi))
+    bnd = None if bnd is None else np.ascontiguousarray(bnd, float)
+    rc = lib().hs_solve_batch(model, prec, C.byref(o), B, _dp(x0), _dp(yref), _dp(p), _dp(x), _dp(u), _dp(pi), _ip(st), _ip(si), _ip(qi),
+                              _dp(bnd))
     assert rc == 0, rc
     return dict(x=x, u=u, pi=pi, status=st, sqp_iter=si, qp_iter=qi)
 

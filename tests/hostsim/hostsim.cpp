@@ -39,7 +39,7 @@ struct Sim {
         ints.assign((size_t)4 * B, 0);
         gs.status = ints.data(); gs.sqp_iter = gs.status + B; gs.qp_iter = gs.sqp_iter + B; gs.have_mult = gs.qp_iter + B;
         gs.B = B; gs.N = N;
-        u0.assign((size_t)B * M::NU, 0.0); gs.U0 = u0.data();
+        u0.assign((size_t)B * M::NU, 0.0); gs.U0 = u0.data(); gs.BND = nullptr;
         sm.assign(SmLayout<M, true>::elems(N), T(0));
     }
     void set(int inst, int field, int k, const double* v) {
@@ -54,10 +54,11 @@ struct Sim {
 
 template <class M, class T>
 static int solve_batch_t(const Opts* o, int B, const double* x0, const double* yref, const double* p, double* x, double* u,
-                         double* pi, int* status, int* sqp_iter, int* qp_iter) {
+                         double* pi, int* status, int* sqp_iter, int* qp_iter, const double* bnd) {
     constexpr int NX = M::NX, NU = M::NU, ny = NX + NU;
     const int N = o->N;
     Sim<M, T> sim(B, N);
+    sim.gs.BND = const_cast<double*>(bnd);          // per-stage bounds [B][N][2][NU+NX] or NULL
     HostGroup g;
     for (int i = 0; i < B; i++) {
         for (int k = 0; k <= N; k++) sim.set(i, F_X, k, x + ((size_t)i * (N + 1) + k) * NX);
@@ -203,8 +204,8 @@ void hs_circle_table(int B, int rows, int n, const double* prm, double* out) {
 }
 // AoS in/out like the C oracle's orc_solve_batch: x [B][N+1][NX], u [B][N][NU] (start iterate in, solution out)
 int hs_solve_batch(int model, int prec, const Opts* o, int B, const double* x0, const double* yref, const double* p, double* x,
-                   double* u, double* pi, int* status, int* sqp_iter, int* qp_iter) {
-    DISPATCH(solve_batch_t, model, prec, o, B, x0, yref, p, x, u, pi, status, sqp_iter, qp_iter)
+                   double* u, double* pi, int* status, int* sqp_iter, int* qp_iter, const double* bnd) {
+    DISPATCH(solve_batch_t, model, prec, o, B, x0, yref, p, x, u, pi, status, sqp_iter, qp_iter, bnd)
 }
 // batch-minor in/out exactly like bnmpc_closed_loop_* (x0 [4][B], p_* [2][B], ref shared [rows][8] or [rows][8][B], logs [steps][dim][B])
 int hs_closed_loop(int model, int prec, const Opts* o, int B, int n_steps, int rows, const double* ref, int ref_shared,

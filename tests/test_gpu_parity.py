@@ -105,7 +105,9 @@ def test_fused_loop_reproduces_reference_run(model, lo):
 def test_reference_style_main_reproduces_reference_run():
     """The reference's own driver shape: np.random.seed(42); main(x0) -> force then jerk follow_trajectory through the
     AcadosOcpSolver/AcadosSimSolver-style shims (set/solve/get per step, B = 1, numpy in/out)."""
-    from drone_attitude_control_b200.main import main
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'examples', 'reference_style'))
+    from main import main
     np.random.seed(42)
     out = main(X0_MAIN.copy(), verbose=False)
     for model in ('force', 'jerk'):
@@ -116,6 +118,26 @@ def test_reference_style_main_reproduces_reference_run():
         assert _gold_err(r['Xsim'][:, 0], g, 'px') < 1e-7 and _gold_err(r['Xsim'][:, 1], g, 'pz') < 1e-7
     assert out['force']['cost'] == pytest.approx(66.3063, abs=1e-3)
     assert out['jerk']['cost'] == pytest.approx(456.636, abs=1e-2)
+
+
+def test_package_follow_trajectory_reproduces_reference_run():
+    """force_model / jerk_model.follow_trajectory of the package (the reference's signature over the fused loop, B = 1, all 500
+    steps in one launch) with numpy's global stream seeded like main.py: the decoded acados series again."""
+    from drone_attitude_control_b200 import force_model, jerk_model
+    from drone_attitude_control_b200.generate_trajectory import gen_circle_traj
+    ref = gen_circle_traj(500, 30, nx=6, nu=2, center=[0, 0], radius=1)
+    np.random.seed(42)
+    cf, xf, af, uf = force_model.follow_trajectory(ref[:, :4], ref[:, 4:6], X0_MAIN.copy(), True)
+    cj, xj, aj, uj = jerk_model.follow_trajectory(ref[:, :6], ref[:, 6:], X0_MAIN.copy(), True)
+    for (c, x, u, tag, cost, tol) in ((cf, xf, uf, 'force', 66.3063, 1e-3), (cj, xj, uj, 'jerk', 456.636, 1e-2)):
+        g = np.load(os.path.join(GOLD, f'acados_{tag}.npz'))
+        assert _gold_err(u[:, 0], g, 'theta') < 5e-7 and _gold_err(u[:, 1], g, 'Fd') < 1e-7
+        assert _gold_err(x[:, 0], g, 'px') < 1e-7 and _gold_err(x[:, 1], g, 'pz') < 1e-7
+        assert c == pytest.approx(cost, abs=tol)
+    ocp = force_model.OCP(batch=2)
+    ocp.create_ocp(ubu=[0.3, 0.35])                      # the OCP can be described, not only selected
+    ocp.create_ocp_solver()
+    assert list(ocp.ocp_solver.cfg.ubu)[:2] == [0.3, 0.35]
 
 
 def test_sharding_is_bit_invariant():
@@ -147,7 +169,7 @@ def test_edge_cases_and_error_conventions():
     with pytest.raises(ValueError):
         s.set(0, 'nope', np.zeros((3, 4)))
     with pytest.raises(ValueError):
-        s.set(5, 'lbx', np.zeros((3, 4)))           # x0 embedding exists at stage 0 only
+        s.set(30, 'lbx', np.zeros((3, 4)))          # state boxes exist at stages 0 (x0 embedding) .. N-1 only
     with pytest.raises(ValueError):
         s.set(0, 'yref', np.zeros((3, 5)))          # wrong dimension
     with pytest.raises(pkg.BnmpcError):
@@ -367,9 +389,12 @@ def test_nonlinear_thrust_ocp_matches_oracle():
     want = co.closed_loop(oo, refs, x0, noise, pc, pp, S)
     got, _ = _run_loop('thrust', refs, x0, noise, pc, pp, S)
     assert np.array_equal(got['status'], want['status']) and np.array_equal(got['qp_iter'], want['qp_iter'])
-    # Full-step SQP on a nonlinear OCP can amplify round-off on individual instances (the host build of the very same
-    # templates shows it against the oracle too, e.g. 1.7e-5 on one of these 32): at least 90 % of the instances must
-    # agree to 1e-9, all of them to 1e-3; statuses and iteration counts agree everywhere (asserted above).
+    # A cold solve of this OCP takes 20-100 full-step SQP iterations (no globalisation, like the reference's fixed full step)
+    # and the iteration is not contractive far from the solution: round-off differences of 1e-14 per iteration are amplified
+    # on individual instances (3e-5 on one of these 32, in the host build of the same templates too).  That it is
+    # amplification and not a defect is shown by test_nonlinear_ocp_one_iteration_from_identical_iterates below: every single
+    # iteration from identical iterates agrees to 1e-9.  Here: at least 90 % of the instances agree to 1e-9 over the whole
+    # loop, all of them to 1e-3; statuses and iteration counts agree everywhere (asserted above).
     dev = np.max(np.abs(got['Xsim'] - want['Xsim']), axis=(1, 2))
     assert (dev <= 1e-9).mean() >= 0.9 and dev.max() <= 1e-3, np.sort(dev)[-4:]
     tight = dev <= 1e-9
@@ -590,3 +615,98 @@ def test_work_queue_ring_wraps():
             s.solve_for_x0_device(x0t, ud, sd)
     s.synchronize()
     assert s.launch_count() >= 2300
+
+
+def test_per_stage_bounds_through_the_api():
+    """ocp_solver.set(stage, 'lbu' | 'ubu' | 'lbx' | 'ubx', v) at any stage (acados accepts them; the reference fixes its
+    boxes in create_ocp, src/force_model/ocp.py:62-76): per-instance storage that appears with the first such set(), a
+    second instantiation of the solve kernel, get() round trip, results against the dense-KKT numpy oracle, and the error
+    conventions around them."""
+    from test_hostsim import _stage_bound_case
+    x0, yref, bnd, want = _stage_bound_case()
+    s = pkg.BatchedAcadosOcpSolver('force', batch=2, device=0, numpy_io=True)
+    np.testing.assert_allclose(s.get(4, 'ubu'), np.full((2, 2), 1.3 * o.GRAVITY), rtol=1e-15)       # configuration boxes until set
+    np.testing.assert_allclose(s.get(7, 'lbx'), np.tile([-1.2, -1.2, -1, -1], (2, 1)), rtol=0)
+    s.set_yref_all(yref)
+    for k in range(30):
+        s.set(k, 'lbu', bnd[:, k, 0, :2]); s.set(k, 'ubu', bnd[:, k, 1, :2])
+        if k >= 1:
+            s.set(k, 'lbx', bnd[:, k, 0, 2:]); s.set(k, 'ubx', bnd[:, k, 1, 2:])
+    np.testing.assert_array_equal(s.get(5, 'ubu'), bnd[:, 5, 1, :2])
+    np.testing.assert_array_equal(s.get(6, 'ubx'), bnd[:, 6, 1, 2:])
+    s.set(0, 'lbx', x0); s.set(0, 'ubx', x0)
+    st = s.solve()
+    qp = s.get_stats('qp_iter')
+    for i in range(2):
+        assert st[i] == want[i]['status'] == 0 and qp[i] == want[i]['qp_iter']
+        for k in range(30):
+            np.testing.assert_allclose(s.get(k, 'u')[i], want[i]['u'][k], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(s.get(k, 'x')[i], want[i]['x'][k], rtol=0, atol=1e-9)
+    u0 = s.solve_for_x0(x0)                                  # the one-call form uses the same kernel
+    np.testing.assert_allclose(u0, np.stack([w['u'][0] for w in want]), rtol=0, atol=1e-9)
+    with pytest.raises(ValueError):
+        s.set(30, 'lbu', bnd[:, 0, 0, :2])                   # no input at the terminal stage
+    with pytest.raises(ValueError):
+        s.set(30, 'ubx', bnd[:, 0, 1, 2:])                   # no state box at the terminal stage (no lbx_e in the reference)
+    with pytest.raises(ValueError):
+        s.set(3, 'lbu', np.zeros((2, 3)))                    # wrong dimension
+    L = pkg.lib()
+    import ctypes as C
+    v = np.zeros((2, 2))
+    assert L.bnmpc_set(s.handle, 2, 6, C.c_void_p(v.ctypes.data), 0) == -2 and b'read-only' in L.bnmpc_last_error()     # 'pi'
+    assert L.bnmpc_set(s.handle, 2, 17, C.c_void_p(v.ctypes.data), 0) == -2                                            # unknown field
+    assert L.bnmpc_set(s.handle, -1, 8, C.c_void_p(v.ctypes.data), 0) == -3                                            # stage out of range
+    assert L.bnmpc_set(s.handle, 2, 8, None, 0) == -1                                                                  # NULL
+    loop = pkg.BatchedClosedLoop('force', batch=2, device=0)
+    loop.solver.set(3, 'ubu', np.full((2, 2), 0.3))
+    loop.init(torch.tensor(x0.T.copy()), torch.tensor(o.gen_circle_traj()), n_steps=3)
+    with pytest.raises(pkg.BnmpcError):                       # the fused loop keeps the reference's fixed boxes
+        loop.run()
+
+
+def test_nonlinear_ocp_one_iteration_from_identical_iterates():
+    """The general nonlinear path (per-stage sensitivities, QP, full step) on the device, one SQP iteration at a time from the
+    iterates the oracle visits along a closed loop (uploaded through set(k, 'x' | 'u')): u, x, pi within 1e-9 and equal
+    interior-point iteration counts for every one of them."""
+    from test_hostsim import thrust_iterate_chain
+    B = 24
+    s = pkg.BatchedAcadosOcpSolver('thrust', batch=B, device=0, rti=True, numpy_io=True)
+
+    def one(xs, yref, p, x, u):
+        s.reset()
+        for k in range(31):
+            s.set(k, 'x', x[:, k])
+        for k in range(30):
+            s.set(k, 'u', u[:, k])
+        s.set_yref_all(yref); s.set(0, 'lbx', xs); s.set(0, 'ubx', xs)
+        s.solve()
+        return dict(x=np.stack([s.get(k, 'x') for k in range(31)], 1), u=np.stack([s.get(k, 'u') for k in range(30)], 1),
+                    pi=np.stack([s.get(k, 'pi') for k in range(30)], 1), qp_iter=s.get_stats('qp_iter'))
+
+    worst, nit = thrust_iterate_chain(one, S=3, B=B)
+    assert nit >= 40 and worst < 1e-9, (worst, nit)
+
+
+def test_irk_integrator_on_device():
+    """erk_stages = 0: acados IRK (Gauss-Legendre, 4 stages, Newton, IFT sensitivities), the integrator_type of the reference's
+    force OCP (src/force_model/ocp.py:85), as device code.  The force closed loop integrated with it equals the ERK4 loop
+    (both are the exact discretisation of the affine model) and the oracle's; the thrust OCP with it matches the oracle's IRK."""
+    B, S = 40, 10
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=41, mass_sigma=0.05)
+    erk, _ = _run_loop('force', refs, x0, noise, pc, pp, S)
+    irk, _ = _run_loop('force', refs, x0, noise, pc, pp, S, erk_stages=0)
+    want = co.closed_loop(co.default_opts(co.MODEL_FORCE, erk_stages=0), refs, x0, noise, pc, pp, S)
+    for r in (erk, want):
+        assert np.array_equal(irk['status'], r['status']) and np.array_equal(irk['qp_iter'], r['qp_iter'])
+        np.testing.assert_allclose(irk['Xsim'], r['Xsim'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(irk['U_ctrl'], r['U_ctrl'], rtol=0, atol=1e-9)
+    B = 16
+    oo = co.default_opts(co.MODEL_THRUST, erk_stages=0)
+    xs, yref = thrust_solve_inputs(B, seed=17)
+    w = co.solve_batch(oo, xs, yref, np.repeat(P_NOM[None], B, 0))
+    s = pkg.BatchedAcadosOcpSolver('thrust', batch=B, device=0, erk_stages=0)
+    s.set_yref_all(yref); s.set(0, 'lbx', xs); s.set(0, 'ubx', xs)
+    assert np.array_equal(s.solve().cpu().numpy(), w['status'])
+    assert np.array_equal(s.get_stats('sqp_iter').cpu().numpy(), w['sqp_iter']) and np.array_equal(s.get_stats('qp_iter').cpu().numpy(), w['qp_iter'])
+    ok = w['sqp_iter'] <= 12                              # (long full-step SQP runs amplify round-off, see the thrust test above)
+    np.testing.assert_allclose(s.get(0, 'u').cpu().numpy()[ok], w['u'][ok, 0], rtol=0, atol=1e-8)

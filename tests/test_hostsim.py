@@ -171,3 +171,83 @@ def test_irk_integrator_in_the_product_templates(model):
         assert np.array_equal(got['qp_iter'], ref['qp_iter'])
         np.testing.assert_allclose(got['u'], ref['u'], rtol=0, atol=1e-10)
         np.testing.assert_allclose(got['x'], ref['x'], rtol=0, atol=1e-10)
+
+
+def _stage_bound_case(seed=21, N=30):
+    """a force-model solve whose input box is tightened on stages 3..9 and whose vx box is tightened on stages 5..12"""
+    from oracle import nmpc_oracle as o
+    x0, yref = random_solve_inputs(0, 2, seed=seed)
+    spec = o.force_ocp()
+    bnd = np.zeros((2, N, 2, 6))
+    bnd[:, :, 0, :2], bnd[:, :, 1, :2] = spec.lbu, spec.ubu
+    bnd[:, :, 0, 2:], bnd[:, :, 1, 2:] = spec.lbx, spec.ubx
+    bnd[:, 3:10, 1, :2] = 0.30                 # ubu
+    bnd[:, 3:10, 0, 1] = 0.25                  # lbu of F_z
+    bnd[0, 5:13, 1, 4] = 0.2; bnd[0, 5:13, 0, 4] = -0.2      # |vx| <= 0.2 for instance 0
+    want = []
+    for i in range(2):
+        s = o.OracleOcpSolver(spec)
+        for k in range(N):
+            s.set(k, 'yref', yref[i, k * 6:(k + 1) * 6])
+            s.set(k, 'lbu', bnd[i, k, 0, :2]); s.set(k, 'ubu', bnd[i, k, 1, :2])
+            if k >= 1:
+                s.set(k, 'lbx', bnd[i, k, 0, 2:]); s.set(k, 'ubx', bnd[i, k, 1, 2:])
+        s.set(N, 'yref', yref[i, 180:])
+        s.set(0, 'lbx', x0[i]); s.set(0, 'ubx', x0[i])
+        st = s.solve()
+        want.append(dict(status=st, u=s.u.copy(), x=s.x.copy(), qp_iter=s.qp_iter, sqp_iter=s.sqp_iter))
+    return x0, yref, bnd, want
+
+
+def test_per_stage_bounds_match_numpy_oracle():
+    """'lbu' / 'ubu' / 'lbx' / 'ubx' set per stage (acados' ocp_solver.set at any stage): the product templates with the
+    per-stage lookup compiled in against the dense-KKT numpy oracle."""
+    x0, yref, bnd, want = _stage_bound_case()
+    p = np.repeat(np.array([[0.03277, 9.81]]), 2, 0)
+    oo = hs.opts_from_oracle(co.default_opts(0))
+    got = hs.solve_batch(0, hs.FP64, oo, x0, yref, p, bnd=bnd)
+    free = hs.solve_batch(0, hs.FP64, oo, x0, yref, p)
+    for i in range(2):
+        assert got['status'][i] == want[i]['status'] == 0
+        assert got['qp_iter'][i] == want[i]['qp_iter'] and got['sqp_iter'][i] == want[i]['sqp_iter']
+        np.testing.assert_allclose(got['u'][i], want[i]['u'], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(got['x'][i], want[i]['x'], rtol=0, atol=1e-9)
+        assert got['u'][i, 3:10].max() <= 0.30 + 1e-9 and got['u'][i, 3:10, 1].min() >= 0.25 - 1e-9
+    assert np.abs(got['x'][0, 5:13, 2]).max() <= 0.2 + 1e-9
+    assert np.abs(got['u'] - free['u']).max() > 1e-3          # the per-stage boxes changed the solution
+
+
+def thrust_iterate_chain(solve_one_iteration, S=3, B=24, seed=19):
+    """Walk the SQP iterates of the nonlinear thrust OCP along a closed loop as the ORACLE visits them and hand every iterate
+    to `solve_one_iteration(xs, yref, p, x, u) -> dict(x, u, pi, qp_iter)` (one SQP iteration = SQP_RTI from that iterate):
+    returns the worst deviation of a single iteration from identical iterates and the number of iterations compared.  Used by
+    the host-emulation test below and by the GPU parity test: it separates the parity of ONE iteration (linearisation with
+    per-stage sensitivities, QP, full step - must agree to 1e-9) from the amplification of round-off over the 20-100
+    full-step iterations a cold solve of this OCP takes (which is why accumulated closed-loop states carry a looser bound)."""
+    from common import random_loop_inputs, thrust_refs
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=seed, mass_sigma=0.05)
+    refs = thrust_refs(refs)
+    oo, orti = co.default_opts(co.MODEL_THRUST), co.default_opts(co.MODEL_THRUST, rti=True)
+    N = 30
+    x, u, xs = np.zeros((B, N + 1, 4)), np.zeros((B, N, 2)), x0.copy()
+    worst, nit = 0.0, 0
+    for i in range(S):
+        yref = np.concatenate([refs[:, i:i + N, :6].reshape(B, -1), refs[:, i + N, :4]], 1)
+        full = co.solve_batch(oo, xs, yref, pc, x=x, u=u)
+        xi, ui = x.copy(), u.copy()
+        for _ in range(min(int(full['sqp_iter'].max()), 40)):
+            a = co.solve_batch(orti, xs, yref, pc, x=xi, u=ui)
+            b = solve_one_iteration(xs, yref, pc, xi, ui)
+            assert np.array_equal(a['qp_iter'], b['qp_iter'])
+            worst = max(worst, np.abs(a['u'] - b['u']).max(), np.abs(a['x'] - b['x']).max(), np.abs(a['pi'] - b['pi']).max())
+            nit += 1
+            xi, ui = a['x'], a['u']
+        x, u = full['x'], full['u']
+        xs = co.sim_batch(xs, u[:, 0][:, None, :], pp, 4, 1, 0.02) + noise[i][:, None]
+    return worst, nit
+
+
+def test_nonlinear_ocp_one_iteration_from_identical_iterates():
+    ho = hs.opts_from_oracle(co.default_opts(co.MODEL_THRUST, rti=True))
+    worst, nit = thrust_iterate_chain(lambda xs, yref, p, x, u: hs.solve_batch(hs.MODEL_THRUST, hs.FP64, ho, xs, yref, p, x=x, u=u), S=2, B=8)
+    assert nit >= 20 and worst < 1e-9, (worst, nit)
