@@ -367,15 +367,31 @@ def run_e2e(args, pkg, dev, local, inp, ref_im, world, barrier, allmax, Ke):
             ydev[i % 2].copy_(yh[i], non_blocking=True)
             yev[i % 2].record(copy_stream)
 
+    x0b = [pin(B, nx), pin(B, nx)]
+
     def start():
         s.reset()
         xs_h.copy_(inp['x0'].t())
         acc[:, 0] = 0.0; acc[:, 1] = 9.81
+        x0b[0][:, :4] = xs_h
+        if jerk:
+            x0b[0][:, 4:] = acc
         prefetch(0)
 
-    def step(i, last):
+    def step_fused(i, last):
+        """one C-ABI call per control step: x0 + noise in; solve, Converter, plant step on the device; u0, u_plant, status and
+        the next x0 out"""
         torch.cuda.current_stream().wait_event(yev[i % 2])
         s.set_yref_all(ydev[i % 2])                                      # OCP.set_up_ocp
+        s.step_into(x0b[i % 2], noise_h[i], u_host, up_h[:, 0], st_host, x0b[(i + 1) % 2], wait=False)
+        if not last:
+            prefetch(i + 1)
+        s.synchronize()
+
+    def step_calls(i, last):
+        """the reference's call sequence: solve_for_x0, Converter on the host, simulate_next_x"""
+        torch.cuda.current_stream().wait_event(yev[i % 2])
+        s.set_yref_all(ydev[i % 2])
         x0h[:, :4] = xs_h
         if jerk:
             x0h[:, 4:] = acc
@@ -393,22 +409,35 @@ def run_e2e(args, pkg, dev, local, inp, ref_im, world, barrier, allmax, Ke):
         s.simulate_next_x_into(xs_h, up_h, noise_h[i], xn_h, wait=True)  # OCP.simulate_next_x incl. the noise draw
         xs_h.copy_(xn_h)
 
-    start()
-    for i in range(W):
-        step(i, False)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(W, W + Ke):
-        step(i, i == W + Ke - 1)
-    barrier()
-    dt = allmax(time.perf_counter() - t0)
+    def run(step):
+        start()
+        for i in range(W):
+            step(i, False)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(W, W + Ke):
+            step(i, i == W + Ke - 1)
+        barrier()
+        return allmax(time.perf_counter() - t0)
+
+    dt_calls = run(step_calls)
+    x_calls = xs_h.clone()
+    dt = run(step_fused)
+    same = float((x0b[(W + Ke) % 2][:, :4] - x_calls).abs().max())     # both paths walked the same closed loop
     bad = int((st_host != 0).sum())
     return {'value': world * B * Ke / dt, 'unit': UNIT, 'steps': Ke, 'ms_per_step': dt / Ke * 1e3,
-            'h2d_bytes_per_step': int(B * (per + nx + 4 + 2 * nsub + 1) * 8), 'd2h_bytes_per_step': int(B * (nu * 8 + 4 + 4 * 8)),
+            'h2d_bytes_per_step': int(B * (per + nx + 1) * 8), 'd2h_bytes_per_step': int(B * (nu * 8 + 2 * 8 + 4 + nx * 8)),
             'nonzero_status_last_step': bad,
-            'api': 'per step: BatchedAcadosOcpSolver.set_yref_all (OCP.set_up_ocp) + solve_for_x0 (x0 in, u0 and status out) + Converter on '
-                   'the host + simulate_next_x (x, u, noise in, x_next out), pinned host buffers; the upload of the next step\'s reference '
-                   'window (known in advance) rides a copy stream behind this step\'s x0 and overlaps the solve'}
+            'api': 'per control step, pinned host buffers: BatchedAcadosOcpSolver.set_yref_all (OCP.set_up_ocp: the yref window, H2D) + '
+                   'step_into = bnmpc_step_for_x0 (x0 and the noise draw in; x0 embedding, solve, get(0,u), Converter.convert and '
+                   'simulate_next_x on the device; u0, u_plant, status and the next x0 out).  The upload of the next step\'s window '
+                   '(known in advance) rides a copy stream behind this step\'s x0 and overlaps the solve',
+            'reference_call_sequence': {'value': world * B * Ke / dt_calls, 'unit': UNIT, 'ms_per_step': dt_calls / Ke * 1e3,
+                                        'h2d_bytes_per_step': int(B * (per + nx + 4 + 2 * nsub + 1) * 8),
+                                        'd2h_bytes_per_step': int(B * (nu * 8 + 4 + 4 * 8)),
+                                        'api': 'solve_for_x0 (x0 in, u0 + status out), Converter on the host, simulate_next_x (x, u, noise in, '
+                                               'x_next out): two device round trips per step, as the reference\'s loop makes them',
+                                        'max_abs_state_difference_to_fused_call': same}}
 
 
 def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):

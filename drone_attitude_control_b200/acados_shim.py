@@ -205,6 +205,14 @@ class BatchedAcadosOcpSolver:
         check(lib().bnmpc_solve_for_x0(self._h, C.c_void_p(x0_dev.data_ptr()), C.c_void_p(u0_dev.data_ptr()),
                                        C.c_void_p(status_dev.data_ptr()), 1))
 
+    def step_into(self, x0_host, eps_host, u0_host, up_host, status_host, xn_host, p_plant_host=None, wait=True):
+        """One iteration of the reference's follow_trajectory for all drones in one call (bnmpc_step_for_x0): x0 embedding,
+        solve, get(0,'u'), Converter.convert, simulate_next_x with the noise draw - pinned host tensors x0 [B, nx], eps [B]
+        (or None) in; u0 [B, nu], u_plant [B, 2], status [B], x_next [B, nx] out (x_next is the next step's x0)."""
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(lib().bnmpc_step_for_x0(self._h, ptr(x0_host), ptr(eps_host), ptr(p_plant_host), ptr(u0_host), ptr(up_host),
+                                      ptr(status_host), ptr(xn_host), 0 if wait else 2))
+
     def simulate_next_x_into(self, x_host, u_host, eps_host, xn_host, p_plant_host=None, wait=True):
         """OCP.simulate_next_x (src/force_model/ocp.py:106-115, src/jerk_model/ocp.py:106-116) for all drones with the plant
         integrator this OCP was configured with (AcadosSim of create_simulator): pinned host tensors x [B, 4], u [B, substeps,

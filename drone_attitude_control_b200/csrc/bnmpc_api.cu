@@ -191,6 +191,39 @@ __global__ void k_sim_step(int B, int ns, int nsub, double hstep, const double* 
     for (int j = 0; j < 4; j++) xn[(size_t)i * 4 + j] = xs[j] + e;
 }
 
+// Converter.convert + OCP.simulate_next_x for every instance from the u0 the solve kernel left in gs.U0 (bnmpc_step_for_x0):
+// force dynamics.py:66-70 / jerk dynamics.py:76-83, then `nsub` plant sub-steps and the noise draw (ocp.py:106-115).
+// x0 [B][nx] = plant state (+ carried acceleration a_i for the jerk model); out_x [B][nx] the same after the step.
+__global__ void k_convert_sim(int B, int kind, int nx, int ns, int nsub, double hstep, const double* x0, const double* u0, const double* par_mass,
+                              int par_stride, int par_is_float, const double* p_plant, const double* eps, double* out_x, double* out_up) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    double xs[4], pp[2] = {0.03277, 9.81}, up[2] = {0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < 4; j++) xs[j] = x0[(size_t)i * nx + j];
+    if (p_plant) { pp[0] = p_plant[(size_t)i * 2]; pp[1] = p_plant[(size_t)i * 2 + 1]; }
+    const double u[2] = {u0[(size_t)i * 2], u0[(size_t)i * 2 + 1]};
+    if (kind == KIND_JERK) {
+        const double mass = par_is_float ? (double)((const float*)par_mass)[(size_t)i * par_stride] : par_mass[(size_t)i * par_stride];
+        double ai[2] = {x0[(size_t)i * nx + 4], x0[(size_t)i * nx + 5]};
+        for (int j = 0; j < nsub; j++) {
+            ai[0] += u[0] * hstep; ai[1] += u[1] * hstep;
+            const double fx = mass * ai[0], fz = mass * ai[1];
+            up[0] = atan2(fx, fz); up[1] = sqrt(fx * fx + fz * fz);
+            plant_step<double>(ns, pp, hstep, up, xs);
+        }
+        out_x[(size_t)i * nx + 4] = ai[0]; out_x[(size_t)i * nx + 5] = ai[1];
+    } else {
+        if (kind == KIND_THRUST) { up[0] = u[0]; up[1] = u[1]; }
+        else { up[0] = atan2(u[0], u[1]); up[1] = sqrt(u[0] * u[0] + u[1] * u[1]); }
+        for (int j = 0; j < nsub; j++) plant_step<double>(ns, pp, hstep, up, xs);
+    }
+    const double e = eps ? eps[i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) out_x[(size_t)i * nx + j] = xs[j] + e;
+    out_up[(size_t)i * 2] = up[0]; out_up[(size_t)i * 2 + 1] = up[1];
+}
+
 // gen_circle_traj for every instance, written instance-major [B][rows][8] with the arithmetic the solver uses on the fly
 __global__ void k_circle_table(int B, int rows, int n, const double* prm, double* out) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -673,6 +706,56 @@ int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* stat
     if (u0) CK(cudaMemcpyAsync(u0, h->gs.U0, sizeof(double) * B * nu, out, h->stream));   // gathered by the solve kernel
     if (status) CK(cudaMemcpyAsync(status, h->gs.status, sizeof(int32_t) * B, out, h->stream));
     if (!on_device) CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int bnmpc_step_for_x0(void* handle, const double* x0, const double* eps, const double* p_plant, double* u0, double* u_plant,
+                      int32_t* status, double* x_next, int on_device) {
+    Handle* h = (Handle*)handle;
+    if (!h || !x0 || !x_next) return fail(BNMPC_E_ARG, "NULL argument");
+    if (on_device < 0 || on_device > BNMPC_HOST_ASYNC) return fail(BNMPC_E_ARG, "on_device must be 0, 1 or BNMPC_HOST_ASYNC");
+    if (use_device(h)) return BNMPC_E_CUDA;
+    const int B = h->batch, nx = h->ops->nx, nu = h->ops->nu;
+    const bool dev = on_device == 1;
+    const cudaMemcpyKind out = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    // inputs: x0 | p_plant | eps in one staging buffer (host modes)
+    const size_t n0 = (size_t)B * nx, n1 = p_plant ? (size_t)B * 2 : 0, n2 = eps ? (size_t)B : 0;
+    const double *dx = x0, *dp = p_plant, *de = eps;
+    if (!dev) {
+        if (h->stage_cap[3] < n0 + n1 + n2) {
+            if (h->stage[3]) CK(cudaFree(h->stage[3]));
+            h->stage[3] = nullptr; h->stage_cap[3] = 0;
+            CK(cudaMalloc(&h->stage[3], (n0 + n1 + n2) * sizeof(double)));
+            h->stage_cap[3] = n0 + n1 + n2;
+        }
+        double* d = h->stage[3];
+        CK(cudaMemcpyAsync(d, x0, n0 * 8, cudaMemcpyHostToDevice, h->stream));
+        if (p_plant) CK(cudaMemcpyAsync(d + n0, p_plant, n1 * 8, cudaMemcpyHostToDevice, h->stream));
+        if (eps) CK(cudaMemcpyAsync(d + n0 + n1, eps, n2 * 8, cudaMemcpyHostToDevice, h->stream));
+        dx = d; dp = p_plant ? d + n0 : nullptr; de = eps ? d + n0 + n1 : nullptr;
+    }
+    // lbx_0 = ubx_0 = x0_bar
+    if (h->ops->elem_size == 8) CK(cudaMemcpyAsync(h->gs.X0, dx, n0 * 8, cudaMemcpyDeviceToDevice, h->stream));
+    else CK(field_xfer(h, F_LBX, 0, const_cast<double*>(dx), nx, nx, 1));
+    if (int rc = refresh_order(h)) return rc;
+    int* q;
+    if (int rc = next_queue(h, &q)) return rc;
+    CK((h->gs.BND ? h->ops->solve_sb : h->ops->solve)(h->gs, h->opts, h->ctas, h->warps, q, h->stream)); h->launches++;
+    // Converter + plant step + noise on the device, results staged as x_next | u_plant
+    double* dout;
+    if (int rc = stage_out_begin(h, 1, nullptr, n0 + (size_t)B * 2, 0, &dout)) return rc;
+    double* dxn = dev ? x_next : dout;
+    double* dup = (dev && u_plant) ? u_plant : dout + n0;
+    k_convert_sim<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->ops->kind, nx, h->cfg.sim_erk_stages, h->cfg.sim_substeps, h->cfg.sim_dt, dx, h->gs.U0,
+                                                           (const double*)h->gs.PAR, h->ops->np, h->ops->elem_size == 4, dp, de, dxn, dup);
+    CK(cudaGetLastError()); h->launches++;
+    if (!dev) {
+        CK(cudaMemcpyAsync(x_next, dout, n0 * 8, out, h->stream));
+        if (u_plant) CK(cudaMemcpyAsync(u_plant, dout + n0, (size_t)B * 2 * 8, out, h->stream));
+    }
+    if (u0) CK(cudaMemcpyAsync(u0, h->gs.U0, sizeof(double) * B * nu, out, h->stream));
+    if (status) CK(cudaMemcpyAsync(status, h->gs.status, sizeof(int32_t) * B, out, h->stream));
+    if (on_device == 0) CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

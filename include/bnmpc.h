@@ -142,6 +142,15 @@ int bnmpc_solve(void* handle);
  * next step's reference window behind this step's x0 instead of in front of it). */
 #define BNMPC_HOST_ASYNC 2
 int bnmpc_solve_for_x0(void* handle, const double* x0, double* u0, int32_t* status, int on_device);
+/* One iteration of follow_trajectory (src/force_model/controller.py:26-48, src/jerk_model/controller.py:27-50) for all
+ * instances in ONE call, with the yref set before (bnmpc_set_yref_all): x0 embedding + solve() + get(0,'u') + Converter.convert
+ * + OCP.simulate_next_x including the noise draw.  x0 AoS [batch][nx] (plant state, + the carried acceleration a_i for the
+ * jerk model); eps [batch] or NULL (the np.random.normal(0, noise) draw of each instance); p_plant AoS [batch][2] or NULL
+ * (nominal).  Out: u0 [batch][nu], u_plant [batch][2] = (theta, Fd) of the last sub-step, status [batch], x_next
+ * [batch][nx] = the next step's x0 (any of u0 / u_plant / status may be NULL).  Two kernel launches; on_device as for
+ * bnmpc_solve_for_x0. */
+int bnmpc_step_for_x0(void* handle, const double* x0, const double* eps, const double* p_plant, double* u0, double* u_plant,
+                      int32_t* status, double* x_next, int on_device);
 /* ocp_solver.get_stats / status: int32 [batch] */
 int bnmpc_get_stats(void* handle, int which, int32_t* out, int on_device);
 

@@ -710,3 +710,37 @@ def test_irk_integrator_on_device():
     assert np.array_equal(s.get_stats('sqp_iter').cpu().numpy(), w['sqp_iter']) and np.array_equal(s.get_stats('qp_iter').cpu().numpy(), w['qp_iter'])
     ok = w['sqp_iter'] <= 12                              # (long full-step SQP runs amplify round-off, see the thrust test above)
     np.testing.assert_allclose(s.get(0, 'u').cpu().numpy()[ok], w['u'][ok, 0], rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize('model', ['force', 'jerk'])
+def test_one_call_control_step_matches_the_fused_loop(model):
+    """bnmpc_step_for_x0 = one iteration of the reference's follow_trajectory per call (x0 + noise draw in; x0 embedding, solve,
+    get(0,'u'), Converter.convert, simulate_next_x on the device; u0, u_plant, status and the next x0 out), chained over a
+    closed loop with host buffers: the same trajectory as the fused device-resident loop and as the oracle."""
+    B, S = 50, 8
+    om = MODEL_ID[model]
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=51 + om, mass_sigma=0.05)
+    want = co.closed_loop(co.default_opts(om), refs, x0, noise, pc, pp, S)
+    fused, _ = _run_loop(model, refs, x0, noise, pc, pp, S)
+    s = pkg.BatchedAcadosOcpSolver(model, batch=B, device=0, numpy_io=False)
+    nx, nu, N, ny = s.nx, s.nu, s.N, s.ny
+    pin = lambda *sh, dt=torch.float64: torch.zeros(sh, dtype=dt).pin_memory()
+    xa, xb, u0, up, st = pin(B, nx), pin(B, nx), pin(B, nu), pin(B, 2), pin(B, dt=torch.int32)
+    ppt = torch.tensor(pp).pin_memory()
+    xa[:, :4] = torch.tensor(x0)
+    if nx == 6:
+        xa[:, 4] = 0.0; xa[:, 5] = 9.81
+    cols = list(range(8)) if nx == 6 else list(range(6))
+    X = [x0.copy()]
+    for i in range(S):
+        y = np.concatenate([refs[:, i:i + N, cols].reshape(B, N * ny), refs[:, i + N, :nx]], 1)
+        s.set_yref_all(torch.tensor(y))
+        s.step_into(xa, torch.tensor(noise[i]).pin_memory(), u0, up, st, xb, p_plant_host=ppt)
+        assert np.array_equal(st.numpy(), want['status'][:, i])
+        np.testing.assert_allclose(u0.numpy(), want['U_ctrl'][:, i], rtol=0, atol=1e-9)
+        np.testing.assert_allclose(up.numpy(), want['U_plant'][:, i], rtol=0, atol=1e-9)
+        X.append(xb[:, :4].numpy().copy())
+        xa, xb = xb, xa
+    X = np.stack(X, 1)
+    np.testing.assert_allclose(X, want['Xsim'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(X, fused['Xsim'], rtol=0, atol=1e-12)
