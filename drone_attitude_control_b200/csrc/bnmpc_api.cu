@@ -28,7 +28,8 @@ struct Handle {
     bnmpc_config cfg;
     Opts opts;
     const ModelOps* ops;
-    int batch, device, ctas, warps;    // persistent CTAs per launch (one per SM) and warps per CTA (instances in flight per SM)
+    int batch, device, ctas, warps;    // persistent CTAs per launch (one per SM) and instances per CTA (in flight per SM)
+    int wpg;                       // warps per instance of the closed-loop kernel (1 at the reference horizon, 2 / 4 for long horizons)
     int *queue, qi;                // work-queue counters (one per launch, recycled), next counter to use
     int* order;                    // queue position -> instance, refreshed before every launch (longest expected solve first)
     cudaStream_t stream;
@@ -472,7 +473,7 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
         return fail(BNMPC_E_CUDA, "no CUDA device: libbnmpc has no CPU path");
     if (device < 0 || device >= ndev) return fail(BNMPC_E_ARG, "device index out of range");
-    if (ops->smem_bytes(cfg->horizon) > 226 * 1024 || ops->tmem_cols(cfg->horizon, 1) == 0)
+    if (ops->smem_bytes(cfg->horizon) > 226 * 1024 || ops->tmem_cols(cfg->horizon, 1, 1) == 0)
         return fail(BNMPC_E_UNSUPPORTED, "horizon too long: the working set of one instance exceeds 227 KB of shared memory or 512 tensor-memory columns");
     CK(cudaSetDevice(device));
     Handle* h = new Handle();
@@ -521,7 +522,8 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
         int warps = 0;
         cudaDeviceProp pr;
         CKH(cudaGetDeviceProperties(&pr, device));
-        CKH(ops->cta_shape(cfg->horizon, &warps));
+        int wpg = 1;
+        CKH(ops->cta_shape(cfg->horizon, &warps, &wpg));
         if (warps < 1) { bnmpc_destroy(h); return fail(BNMPC_E_UNSUPPORTED, "kernel does not fit on an SM for this horizon"); }
         if (const char* e = getenv("BNMPC_WARPS_PER_SM")) {     // tuning knob: fewer instances in flight per SM than would fit
             const int v = atoi(e);
@@ -530,6 +532,16 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
         if (batch < warps * pr.multiProcessorCount)             // small batches spread over the SMs instead of filling a few
             warps = (batch + pr.multiProcessorCount - 1) / pr.multiProcessorCount;
         h->warps = warps;
+        // warps per instance of the closed-loop kernel: with few instances per SM (long horizon, or a small batch spread over
+        // the SMs) each one gets a group of 2 or 4 warps for its 32-lane passes, up to the launch bound and the tensor memory
+        wpg = 1;
+        for (int g = ops->max_wpg; g >= 2; g /= 2)
+            if (warps * g <= ops->max_warps && ops->tmem_cols(cfg->horizon, warps * g, g) != 0) { wpg = g; break; }
+        if (const char* e = getenv("BNMPC_WARPS_PER_INSTANCE")) {   // tuning knob: 1 switches the warp groups off
+            const int v = atoi(e);
+            if (v >= 1 && v < wpg) wpg = (v >= 2) ? 2 : 1;
+        }
+        h->wpg = wpg;
         const int want = (batch + warps - 1) / warps;
         h->ctas = want < pr.multiProcessorCount ? want : pr.multiProcessorCount;
         // longest-first order: pays from about two instances per warp on (measured: +3 % at 3.5 per warp, +5 % for the jerk
@@ -860,7 +872,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
         if (ns == 1) {
             la.chunk = 1;
             if (h->loop_kernel == 1) CK(h->ops->loop_ls(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream));
-            else CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream));
+            else CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, h->wpg, q, h->stream));
             h->launches++;
         } else {
             const bool ls = h->loop_kernel == 1;
@@ -878,7 +890,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
                 CK(cudaGetLastError()); h->launches++;
             }
             if (ls) CK(h->ops->loop_ls(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream));
-            else CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, q, h->stream));
+            else CK(h->ops->loop_step(h->gs, h->opts, la, h->ctas, h->warps, h->wpg, q, h->stream));
             h->launches++;
         }
         s += ns;

@@ -51,16 +51,18 @@ template <class T> inline Gs<T> gs_cast(const GsAny& a) {
 struct ModelOps {
     const char* name;
     int nx, nu, np, nblk, nxb, nub, kind, jac_const, elem_size, sm_rows;
+    int max_wpg, max_warps;                                         // largest warp group per instance the closed-loop kernel was built for; launch bound
     size_t (*smem_bytes)(int N);                                    // dynamic shared memory of one instance (one warp)
-    int (*tmem_cols)(int N, int warps);                             // tensor-memory columns a CTA of `warps` allocates (0 = too many)
+    int (*tmem_cols)(int N, int warps, int wpg);                    // tensor-memory columns a CTA of `warps` allocates (0 = too many)
     cudaError_t (*solve)(const GsAny&, const Opts&, int ctas, int warps, int* queue, cudaStream_t);
     // the same for handles whose instances carry per-stage bounds (GsAny::BND): a second instantiation of the solve kernel, so
     // that the lookup costs the common case nothing
     cudaError_t (*solve_sb)(const GsAny&, const Opts&, int ctas, int warps, int* queue, cudaStream_t);
-    cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
+    cudaError_t (*loop_step)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int wpg, int* queue, cudaStream_t);
     // slotted lockstep schedule (bnmpc_lockstep.cuh): LoopArgs::n_steps control steps per launch, tickets of LoopArgs::chunk steps
     cudaError_t (*loop_ls)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
-    cudaError_t (*cta_shape)(int N, int* warps);                    // warps per CTA (= instances in flight per SM), 0 = does not fit
+    // warps per CTA and warps per instance (wpg; instances in flight per SM = warps / wpg), warps = 0: does not fit
+    cudaError_t (*cta_shape)(int N, int* warps, int* wpg);
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -114,19 +116,20 @@ struct TmemPriv {
     static constexpr int CPR = CH * 32;                            // columns per round of items
     uint32_t base;                                                 // lane quarter of this warp | first column
 
-    static __host__ __device__ int cols_per_quad(int N) {          // columns the four warps of a quad share (one lane quarter each)
-        return ((N + 1) * M::NBLK + 31) / 32 * CPR;
+    // columns the four warps of a quad share (one lane quarter each); L = lanes of the group that owns an instance
+    static __host__ __device__ int cols_per_quad(int N, int L = 32) {
+        return ((N + 1) * M::NBLK + L - 1) / L * CPR;
     }
-    static __host__ __device__ int cols_needed(int N, int warps) { // allocation of a CTA: power of two >= 32, 0 if it does not fit
-        const int need = (warps + 3) / 4 * cols_per_quad(N);
+    static __host__ __device__ int cols_needed(int N, int warps, int L = 32) { // allocation of a CTA: power of two >= 32, 0 if it does not fit
+        const int need = (warps + 3) / 4 * cols_per_quad(N, L);
         int c = 32;
         while (c < need) c <<= 1;
         return c <= 512 ? c : 0;
     }
     // TMEM address of this warp's records: lane quarter = warp id mod 4 (the hardware's access rule), column group = warp id / 4
-    static __device__ __forceinline__ uint32_t warp_base(uint32_t tbase, int N) {
+    static __device__ __forceinline__ uint32_t warp_base(uint32_t tbase, int N, int L = 32) {
         const uint32_t w = threadIdx.x >> 5;
-        return tbase + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)cols_per_quad(N);
+        return tbase + (((w & 3u) * 32u) << 16) + (w >> 2) * (uint32_t)cols_per_quad(N, L);
     }
     __device__ __forceinline__ void load(T*, int rd, int, bool, PrivRec<T, s, n>& r) const {
         __syncwarp();                                              // tcgen05.ld/st are warp-collective (.aligned)
@@ -214,8 +217,8 @@ __device__ __forceinline__ void tmem_free_cta(uint32_t base, uint32_t cols) {
 // Element offset of this warp's working set inside the CTA's dynamic shared memory.  The value goes through an opaque
 // `mov` so that it lives in ONE register: left to itself the compiler re-derived it from threadIdx and the horizon at
 // every group of shared-memory accesses (16 % of all executed instructions in the ncu profile of that version).
-__device__ __forceinline__ int warp_smem_off(int stride_elems) {
-    int off = stride_elems * (int)(threadIdx.x >> 5);
+__device__ __forceinline__ int warp_smem_off(int stride_elems, int group_lanes = 32) {
+    int off = stride_elems * (int)(threadIdx.x / group_lanes);
     asm volatile("mov.b32 %0, %0;" : "+r"(off));
     return off;
 }
@@ -240,28 +243,41 @@ __device__ __forceinline__ int next_instance(int* queue, const int* order, int B
     return __shfl_sync(0xffffffffu, i, 0);
 }
 
+template <class G>
 struct DevTickets {
-    int* queue; int* next_step;
+    int* queue; int* next_step; const G& g;
+    // value of the group's first lane -> all lanes of the group
+    __device__ __forceinline__ int bcast(int v) const {
+        if constexpr (G::L == 32) return __shfl_sync(0xffffffffu, v, 0);
+        else {
+            __shared__ int word[16];
+            if (g.lane == 0) word[g.gid()] = v;
+            g.sync();
+            v = word[g.gid()];
+            g.sync();
+            return v;
+        }
+    }
     __device__ __forceinline__ int take() const {
         int i = 0;
-        if ((threadIdx.x & 31) == 0) i = atomicAdd(queue, 1);
-        return __shfl_sync(0xffffffffu, i, 0);
+        if (g.lane == 0) i = atomicAdd(queue, 1);
+        return bcast(i);
     }
     __device__ __forceinline__ bool ready(int inst, int step) const {
         int v = 0;
-        if ((threadIdx.x & 31) == 0) v = *(volatile int*)(next_step + inst);
-        v = __shfl_sync(0xffffffffu, v, 0);
+        if (g.lane == 0) v = *(volatile int*)(next_step + inst);
+        v = bcast(v);
         if (v != step) return false;
         __threadfence();
         return true;
     }
-    __device__ __forceinline__ void wait(int inst, int step) const {      // free-running warps only (never inside a CTA-wide schedule)
+    __device__ __forceinline__ void wait(int inst, int step) const {      // free-running groups only (never inside a CTA-wide schedule)
         while (!ready(inst, step)) __nanosleep(200);
     }
     __device__ __forceinline__ void publish(int inst, int next) const {
         __threadfence();
-        __syncwarp();
-        if ((threadIdx.x & 31) == 0) *(volatile int*)(next_step + inst) = next;
+        g.sync();
+        if (g.lane == 0) *(volatile int*)(next_step + inst) = next;
     }
 };
 
@@ -276,22 +292,24 @@ k_solve(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, int* q
     tmem_free_cta(tbase, tmem_cols);
 }
 
-template <class M, class T>
+// WPG warps per instance (see WarpGroup): 1 at the reference horizon, 2 / 4 where the horizon leaves room for only 8 / 4
+// instances per SM
+template <class M, class T, int WPG>
 __global__ void __launch_bounds__(32 * LaunchShape<M, T>::MAX_WARPS, 1)
 k_loop_step(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, const __grid_constant__ LoopArgs a, int* queue, int tmem_cols) {
     const uint32_t tbase = tmem_alloc_cta(tmem_cols);
-    const WarpGroup<32> g;
-    const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N)};
-    Solver<M, T, WarpGroup<32>, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
+    using G = WarpGroup<32 * WPG>;
+    const G g;
+    const TmemPriv<M, T> ps{TmemPriv<M, T>::warp_base(tbase, o.N, G::L)};
+    Solver<M, T, G, TmemPriv<M, T>> sv(nullptr, warp_smem_off(o.smem_stride, G::L), o, g, ps);
     // queue tickets = (instance, chunk of control steps), issued instance-round-robin; with one control step per launch a
     // ticket is simply an instance (one copy of the solver code for both cases: the kernel's hot loop is instruction-fetch
     // sensitive, see profiles/README.md)
-    DevTickets wq{queue, a.next_step};
+    DevTickets<G> wq{queue, a.next_step, g};
     const int total = gs.B * ((a.n_steps + a.chunk - 1) / a.chunk);
     for (int t = wq.take(); t < total; t = wq.take()) closed_loop_chunk<M, T>(sv, t, gs, a, wq);
     tmem_free_cta(tbase, tmem_cols);
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------------
 // slotted lockstep kernel (bnmpc_lockstep.cuh)
@@ -345,7 +363,7 @@ k_loop_ls(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, cons
     SV sv(nullptr, warp_smem_off(o.smem_stride), o, g, ps);
     LsWarp<M, T, WarpGroup<32>, TmemPriv<M, T>> w;
     w.reset();
-    DevTickets wq{queue, a.next_step};
+    DevTickets<WarpGroup<32>> wq{queue, a.next_step, g};
     const int W = (int)(blockDim.x >> 5), warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31);
     static_assert(LaunchShape<M, T>::MAX_WARPS * M::NBLK <= 32, "the sweeps of a CTA must fit one warp");
     const bool prof = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -390,10 +408,11 @@ k_loop_ls(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, cons
     tmem_free_cta(tbase, tmem_cols);
 }
 
-template <class M, class T>
+// GROUPS: also instantiate the closed-loop kernel with 2 and 4 warps per instance (long horizons)
+template <class M, class T, bool GROUPS = false>
 struct OpsImpl {
     static size_t smem_bytes(int N) { return (SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::elems(N) * sizeof(T) + 15) / 16 * 16; }
-    static int tmem_cols(int N, int warps) { return TmemPriv<M, T>::cols_needed(N, warps); }
+    static int tmem_cols(int N, int warps, int wpg) { return TmemPriv<M, T>::cols_needed(N, warps, 32 * wpg); }
     // dynamic shared memory is opted in once per kernel up to the device limit (handles with different horizons share
     // the kernel, so the attribute must not follow the last handle created)
     template <class K>
@@ -409,9 +428,15 @@ struct OpsImpl {
     }
     // Warps of the one CTA per SM = instances in flight per SM: bounded by registers (the launch bound), by shared memory
     // (the opt-in maximum of a block minus the static part) and by tensor memory (512 columns, one column group per warp quad).
-    static cudaError_t cta_shape(int N, int* warps) {
-        cudaError_t e = prep(k_loop_step<M, T>, 0);
+    static cudaError_t cta_shape(int N, int* warps, int* wpg) {
+        cudaError_t e = prep(k_loop_step<M, T, 1>, 0);
         if (e != cudaSuccess) return e;
+        if constexpr (GROUPS) {
+            e = prep(k_loop_step<M, T, 2>, 0);
+            if (e != cudaSuccess) return e;
+            e = prep(k_loop_step<M, T, 4>, 0);
+            if (e != cudaSuccess) return e;
+        }
         e = prep(k_loop_ls<M, T>, 0);
         if (e != cudaSuccess) return e;
         e = prep(k_solve<M, T, false>, 0);
@@ -425,46 +450,55 @@ struct OpsImpl {
         if (e != cudaSuccess) return e;
         int w = (int)((size_t)(optin - 1024) / smem_bytes(N));
         if (w > LaunchShape<M, T>::MAX_WARPS) w = LaunchShape<M, T>::MAX_WARPS;
-        while (w > 0 && tmem_cols(N, w) == 0) w--;
+        while (w > 0 && tmem_cols(N, w, 1) == 0) w--;
         if (w > 4) w = w / 4 * 4;                                // whole warp quads: one warp more on one sub-partition costs more than it adds
         *warps = w;
+        int g = 1;
+        *wpg = g;
         return cudaSuccess;
     }
     static cudaError_t solve(const GsAny& a, const Opts& o_, int ctas, int warps, int* queue, cudaStream_t st) {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
-        k_solve<M, T, false><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps));
+        k_solve<M, T, false><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps, 1));
         return cudaGetLastError();
     }
     static cudaError_t solve_sb(const GsAny& a, const Opts& o_, int ctas, int warps, int* queue, cudaStream_t st) {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
-        k_solve<M, T, true><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps));
+        k_solve<M, T, true><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, queue, tmem_cols(o.N, warps, 1));
         return cudaGetLastError();
     }
-    static cudaError_t loop_step(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int* queue, cudaStream_t st) {
+    // `warps` = instances per CTA, each run by a group of wpg warps
+    static cudaError_t loop_step(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int wpg, int* queue, cudaStream_t st) {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
-        k_loop_step<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N, warps));
+        const int cols = tmem_cols(o.N, warps * wpg, wpg);
+        const size_t sm = smem_bytes(o.N) * warps;
+        if (wpg == 1) k_loop_step<M, T, 1><<<ctas, 32 * warps, sm, st>>>(gs_cast<T>(a), o, la, queue, cols);
+        else if constexpr (GROUPS) {
+            if (wpg == 2) k_loop_step<M, T, 2><<<ctas, 64 * warps, sm, st>>>(gs_cast<T>(a), o, la, queue, cols);
+            else k_loop_step<M, T, 4><<<ctas, 128 * warps, sm, st>>>(gs_cast<T>(a), o, la, queue, cols);
+        } else return cudaErrorInvalidValue;
         return cudaGetLastError();
     }
     static cudaError_t loop_ls(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int* queue, cudaStream_t st) {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
-        k_loop_ls<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N, warps));
+        k_loop_ls<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N, warps, 1));
         return cudaGetLastError();
     }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, &smem_bytes, &tmem_cols, &solve, &solve_sb, &loop_step, &loop_ls, &cta_shape};
+                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, GROUPS ? 4 : 1, LaunchShape<M, T>::MAX_WARPS, &smem_bytes, &tmem_cols, &solve, &solve_sb, &loop_step, &loop_ls, &cta_shape};
     }
 };
 
-#define BNMPC_DEFINE_MODEL_OPS(MODEL, KIND, FN)                                               \
+#define BNMPC_DEFINE_MODEL_OPS(MODEL, KIND, FN, GROUPS)                                       \
     namespace bnmpc {                                                                         \
     const ModelOps* FN(int precision) {                                                       \
-        static const ModelOps d = OpsImpl<MODEL, double>::make(KIND);                          \
-        static const ModelOps f = OpsImpl<MODEL, float>::make(KIND);                           \
+        static const ModelOps d = OpsImpl<MODEL, double, GROUPS>::make(KIND);                  \
+        static const ModelOps f = OpsImpl<MODEL, float, GROUPS>::make(KIND);                   \
         return precision == 0 ? &d : &f;                                                      \
     }                                                                                         \
     }
