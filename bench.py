@@ -288,7 +288,8 @@ def run_ours(args):
     traffic, ncu_view = None, None
     try:       # dram bytes per launch and pipe utilisation of the dominant kernel from the committed ncu capture of this config
         ncu_view = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(f'{args.model}_{args.precision}_B{B}_multistep')
-        traffic = ncu_view.get('traffic_bytes') if ncu_view else None
+        # (the capture covers a launch of `steps_in_capture` control steps: scale to this launch's K steps)
+        traffic = ncu_view['traffic_bytes'] / ncu_view.get('steps_in_capture', 1) * K if ncu_view else None
     except Exception:
         pass
     cfg = config_dict(args)
@@ -320,7 +321,8 @@ def run_ours(args):
     }
     if not args.skip_cpu and world == 1:
         n_inst = min(args.cpu_instances, B)
-        dt, qpm, bad, cores, flags = cpu_closed_loop(args, inp, n_inst, W, args.cpu_steps)
+        inp_cpu = workload(0, n_inst, W + args.cpu_steps, max(500 + N, W + args.cpu_steps + N + 1), N, mass_sigma=args.mass_sigma)   # same ids, more steps
+        dt, qpm, bad, cores, flags = cpu_closed_loop(args, inp_cpu, n_inst, W, args.cpu_steps)
         dense_ratio = flops_per_solve(1, nx, nu, N, erk, 1, 0) / flops_per_solve(nblk, n, m, N, erk, 1, 0)
         line['cpu_baseline'] = {'value': n_inst * args.cpu_steps / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                 'qp_iter_mean': qpm, 'nonzero_status': bad,
@@ -456,12 +458,16 @@ def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):
             peak[prec] = tf.value
         return peak[prec]
 
-    def one(model, total, N, prec, steps, warm, mass_sigma, sharded):
+    def one(model, total, N, prec, steps, warm, mass_sigma, sharded, table=False):
         lo, hi = shard_range(total, rank, world) if sharded else (rank * total, (rank + 1) * total)
         b = hi - lo
         inp = instance_inputs(lo, hi, 0, seed=SEED, mass_sigma=mass_sigma, with_noise=False)
         om = 2 * np.pi / 10
-        cref = pkg.CircleRef(inp['radius'], inp['center'], inp['phase'], n=500)
+        if table:      # per-instance reference tables in HBM, as in the headline configuration
+            from drone_attitude_control_b200.generate_trajectory import gen_circle_traj_batched
+            cref = gen_circle_traj_batched(500, N, inp['radius'], inp['center'], inp['phase'], device=dev).permute(2, 0, 1).contiguous()
+        else:
+            cref = pkg.CircleRef(inp['radius'], inp['center'], inp['phase'], n=500)
         r, ph, c = inp['radius'], inp['phase'], inp['center']
         x0 = torch.stack([c[:, 0] + r * torch.cos(ph), c[:, 1] + r * torch.sin(ph), -r * om * torch.sin(ph), r * om * torch.cos(ph)]) + inp['dx0']
         loop = pkg.BatchedClosedLoop(model, batch=b, device=local, precision=prec, N_horizon=N)
@@ -486,13 +492,14 @@ def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):
         del loop
         torch.cuda.empty_cache()
         return {'model': model, 'instances_total': tot, 'instances_this_rank': b, 'sharded_over_ranks': bool(sharded), 'horizon': N,
-                'precision': prec, 'steps': steps, 'warmup': warm, 'ms': ms, 'value': tot * steps / (ms * 1e-3), 'unit': UNIT,
+                'precision': prec, 'steps': steps, 'warmup': warm, 'ms': ms, 'reference': 'tables in HBM' if table else 'generated in the kernel', 'value': tot * steps / (ms * 1e-3), 'unit': UNIT,
                 'failed_steps': int(st[0]), 'qp_iter_mean_last_step': float(st[1]) / tot,
                 'roofline_frac': ach / fma_peak(prec), 'achieved_tflops': ach}
 
-    out = {'note': 'multi-step launches (steps_per_launch = steps), CircleRef + PhiloxNoise generated in the kernel, CUDA events, max over ranks'}
-    out['config3_jerk_16384_fp64'] = one('jerk', 16384, 30, 'fp64', 20, 5, 0.0, False)
-    out['config3_jerk_16384_fp32'] = one('jerk', 16384, 30, 'fp32', 20, 5, 0.0, False)
+    out = {'note': 'multi-step launches (steps_per_launch = steps), noise drawn in the kernel (PhiloxNoise), reference tables in HBM (config 3) '
+                   'or generated in the kernel (configs 4, 5), CUDA events, max over ranks'}
+    out['config3_jerk_16384_fp64'] = one('jerk', 16384, 30, 'fp64', 20, 5, 0.0, False, table=True)
+    out['config3_jerk_16384_fp32'] = one('jerk', 16384, 30, 'fp32', 20, 5, 0.0, False, table=True)
     out['config4_force_262144_mass_perturbed_sharded'] = dict(one('force', 262144, 30, 'fp64', 10, 3, 0.05, True), scaling='strong')
     for N in (20, 50, 100):
         out[f'config5_force_65536_N{N}'] = one('force', 65536, N, 'fp64', 4 if N > 30 else 8, 2, 0.0, False)
@@ -543,7 +550,7 @@ def main():
     ap.add_argument('--skip-extra', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=50)
     ap.add_argument('--cpu-instances', type=int, default=4096)
-    ap.add_argument('--cpu-steps', type=int, default=60, help='closed-loop steps of the cpu_baseline sample (~10-20 s of CPU work)')
+    ap.add_argument('--cpu-steps', type=int, default=400, help='closed-loop steps of the cpu_baseline sample (~10-20 s of CPU work on 16 cores)')
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
