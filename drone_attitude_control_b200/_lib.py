@@ -6,8 +6,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BNMPC_LIB') or os.path.join(_HERE, 'lib', 'libbnmpc.so')      # BNMPC_LIB: another build of the same library (A/B timing)
 
-MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_THRUST = 0, 1, 2, 3
-MODELS = {'force': MODEL_FORCE, 'jerk': MODEL_JERK, 'force_dense': MODEL_FORCE_DENSE, 'thrust': MODEL_THRUST}
+MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_THRUST, MODEL_ATT = 0, 1, 2, 3, 4
+MODELS = {'force': MODEL_FORCE, 'jerk': MODEL_JERK, 'force_dense': MODEL_FORCE_DENSE, 'thrust': MODEL_THRUST, 'att': MODEL_ATT}
 FP64, FP32 = 0, 1
 # acados return values (reference src/Readme.md:14-20)
 SUCCESS, FAILURE, MAXITER, MINSTEP, QP_FAILURE = 0, 1, 2, 3, 4
@@ -19,8 +19,8 @@ class Config(C.Structure):
     """struct bnmpc_config"""
     _fields_ = [('model', C.c_int32), ('horizon', C.c_int32), ('precision', C.c_int32), ('erk_stages', C.c_int32),
                 ('sqp_max_iter', C.c_int32), ('qp_max_iter', C.c_int32), ('rti', C.c_int32), ('threads_per_block', C.c_int32),
-                ('dt', C.c_double), ('W', C.c_double * 12), ('W_e', C.c_double * 8),
-                ('lbx', C.c_double * 8), ('ubx', C.c_double * 8), ('lbu', C.c_double * 4), ('ubu', C.c_double * 4),
+                ('dt', C.c_double), ('W', C.c_double * 16), ('W_e', C.c_double * 12),
+                ('lbx', C.c_double * 12), ('ubx', C.c_double * 12), ('lbu', C.c_double * 4), ('ubu', C.c_double * 4),
                 ('tol', C.c_double * 4), ('qp_tol', C.c_double * 4),
                 ('mu0', C.c_double), ('thr0', C.c_double), ('alpha_min', C.c_double), ('lam_min', C.c_double), ('t_min', C.c_double),
                 ('sim_erk_stages', C.c_int32), ('sim_substeps', C.c_int32), ('sim_dt', C.c_double)]

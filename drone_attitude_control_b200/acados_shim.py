@@ -213,6 +213,12 @@ class BatchedAcadosOcpSolver:
         check(lib().bnmpc_step_for_x0(self._h, ptr(x0_host), ptr(eps_host), ptr(p_plant_host), ptr(u0_host), ptr(up_host),
                                       ptr(status_host), ptr(xn_host), 0 if wait else 2))
 
+    def step_device(self, x0_dev, eps_dev, u0_dev, up_dev, status_dev, xn_dev, p_plant_dev=None):
+        """step_into with device tensors: everything is enqueued on the solver's stream, nothing synchronises."""
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        check(lib().bnmpc_step_for_x0(self._h, ptr(x0_dev), ptr(eps_dev), ptr(p_plant_dev), ptr(u0_dev), ptr(up_dev),
+                                      ptr(status_dev), ptr(xn_dev), 1))
+
     def simulate_next_x_into(self, x_host, u_host, eps_host, xn_host, p_plant_host=None, wait=True):
         """OCP.simulate_next_x (src/force_model/ocp.py:106-115, src/jerk_model/ocp.py:106-116) for all drones with the plant
         integrator this OCP was configured with (AcadosSim of create_simulator): pinned host tensors x [B, 4], u [B, substeps,
@@ -256,20 +262,23 @@ class BatchedAcadosSimSolver:
     src/jerk_model/ocp.py:97-104): set('x'|'u'|'p', v), solve(), get('x'), simulate(x=, u=).  One solve() is one ERK step
     of length T with `num_stages` stages."""
 
-    def __init__(self, T, num_stages=4, batch=1, device=0, numpy_io=None):
+    def __init__(self, T, num_stages=4, batch=1, device=0, numpy_io=None, model='plant'):
+        """model 'plant': the planar plant of src/plant.py (x [4], u = (theta, Fd)); 'att': the 3-D attitude model as its own
+        plant (x [10], u = (T, wx, wy, wz))."""
         self.device = _require_cuda(device)
         self.batch = int(batch)
         self.numpy_io = (self.batch == 1) if numpy_io is None else bool(numpy_io)
-        cfg = default_config('force', horizon=1, sim_erk_stages=int(num_stages), sim_substeps=1, sim_dt=float(T))
+        self.nx, self.nu = (10, 4) if model == 'att' else (4, 2)
+        cfg = default_config('att' if model == 'att' else 'force', horizon=1, sim_erk_stages=int(num_stages), sim_substeps=1, sim_dt=float(T))
         self._h = C.c_void_p()
         check(lib().bnmpc_create(C.byref(cfg), self.batch, self.device.index, C.byref(self._h)))
         with torch.cuda.device(self.device):
             self._stream = torch.cuda.current_stream()
         check(lib().bnmpc_set_stream(self._h, C.c_void_p(self._stream.cuda_stream)))
-        self._x = torch.zeros((self.batch, 4), dtype=torch.float64, device=self.device)
-        self._u = torch.zeros((self.batch, 2), dtype=torch.float64, device=self.device)
+        self._x = torch.zeros((self.batch, self.nx), dtype=torch.float64, device=self.device)
+        self._u = torch.zeros((self.batch, self.nu), dtype=torch.float64, device=self.device)
         self._p = None
-        self._xn = torch.zeros((self.batch, 4), dtype=torch.float64, device=self.device)
+        self._xn = torch.zeros((self.batch, self.nx), dtype=torch.float64, device=self.device)
 
     def __del__(self):
         h, self._h = getattr(self, '_h', None), None
@@ -289,9 +298,9 @@ class BatchedAcadosSimSolver:
 
     def set(self, field, value):
         if field == 'x':
-            self._x = self._t(value, 4)
+            self._x = self._t(value, self.nx)
         elif field == 'u':
-            self._u = self._t(value, 2)
+            self._u = self._t(value, self.nu)
         elif field == 'p':
             self._p = self._t(value, 2)
         else:

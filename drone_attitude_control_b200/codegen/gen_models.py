@@ -228,6 +228,17 @@ def models():
     # generic coupled path and serve as an in-product cross-check of the block-split path.
     out.append(gen_model('force_dense', [px, pz, vx, vz], [Fx, Fz], [m, g], [vx, vz, Fx / m, Fz / m - g], True))
     out.append(gen_model('jerk_dense', [px, pz, vx, vz, ax, az], [hx, hz], [m, g], [vx, vz, ax, az - g, hx, hz], True))
+    # NOT in the reference (north-star extension): the 3-D attitude-and-total-thrust model - position,
+    # velocity and the attitude quaternion (body -> world) as states, total thrust and the body rates as inputs:
+    #   pdot = v,  vdot = (T / m) R(q) e3 - g e3,  qdot = 1/2 q (x) (0, w)
+    # (the planar plant of src/plant.py:27-33 is its restriction to the x-z plane: theta = pitch, Fd = T)
+    py, vy, qw, qx, qy, qz, Tt, wx, wy, wz = sp.symbols('py vy qw qx qy qz Tt wx wy wz')
+    half = sp.Rational(1, 2)
+    out.append(gen_model('att', [px, py, pz, vx, vy, vz, qw, qx, qy, qz], [Tt, wx, wy, wz], [m, g], [
+        vx, vy, vz,
+        2 * (qx * qz + qw * qy) * Tt / m, 2 * (qy * qz - qw * qx) * Tt / m, (1 - 2 * (qx * qx + qy * qy)) * Tt / m - g,
+        half * (-qx * wx - qy * wy - qz * wz), half * (qw * wx + qy * wz - qz * wy),
+        half * (qw * wy - qx * wz + qz * wx), half * (qw * wz + qx * wy - qy * wx)]))
     return out
 
 

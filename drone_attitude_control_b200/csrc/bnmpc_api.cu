@@ -58,6 +58,7 @@ const ModelOps* pick_ops(int model, int precision) {
     case BNMPC_MODEL_JERK: return ops_jerk(precision);
     case BNMPC_MODEL_FORCE_DENSE: return ops_force_dense(precision);
     case BNMPC_MODEL_THRUST: return ops_thrust(precision);
+    case BNMPC_MODEL_ATT: return ops_att(precision);
     }
     return nullptr;
 }
@@ -190,6 +191,31 @@ __global__ void k_sim_step(int B, int ns, int nsub, double hstep, const double* 
     const double e = eps ? eps[i] : 0.0;
 #pragma unroll
     for (int j = 0; j < 4; j++) xn[(size_t)i * 4 + j] = xs[j] + e;
+}
+
+// the same for the 3-D attitude model (its plant IS the controller model): x [B][10], u [B][nsub][4]; the noise draw is
+// added to position and velocity (the quaternion is left on the unit sphere's neighbourhood the integrator keeps it in)
+__global__ void k_sim_step_att(int B, int ns, int nsub, double hstep, const double* x, const double* u, int u_inst, int u_sub, const double* p_plant,
+                               const double* eps, double* xn) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    constexpr int NX = Model_att::NX, NU = Model_att::NU;
+    double xs[NX], pp[2] = {0.03277, 9.81};
+#pragma unroll
+    for (int j = 0; j < NX; j++) xs[j] = x[(size_t)i * NX + j];
+    if (p_plant) { pp[0] = p_plant[(size_t)i * 2]; pp[1] = p_plant[(size_t)i * 2 + 1]; }
+    const FullFn<Model_att, double> fn{pp};
+    for (int j = 0; j < nsub; j++) {
+        double up[NU], x2[NX], dA[1], dB[1];
+#pragma unroll
+        for (int c = 0; c < NU; c++) up[c] = u[(size_t)i * u_inst + (size_t)j * u_sub + c];
+        erk_dispatch<NX, NU, false>(ns, fn, xs, up, hstep, x2, dA, dB);
+#pragma unroll
+        for (int c = 0; c < NX; c++) xs[c] = x2[c];
+    }
+    const double e = eps ? eps[i] : 0.0;
+#pragma unroll
+    for (int j = 0; j < NX; j++) xn[(size_t)i * NX + j] = xs[j] + (j < 6 ? e : 0.0);
 }
 
 // Converter.convert + OCP.simulate_next_x for every instance from the u0 the solve kernel left in gs.U0 (bnmpc_step_for_x0):
@@ -425,7 +451,7 @@ const char* bnmpc_last_error(void) { return g_err.c_str(); }
 
 int bnmpc_config_default(int model, bnmpc_config* c) {
     if (!c) return fail(BNMPC_E_ARG, "cfg is NULL");
-    if (model < 0 || model > BNMPC_MODEL_THRUST) return fail(BNMPC_E_ARG, "unknown model");
+    if (model < 0 || model > BNMPC_MODEL_ATT) return fail(BNMPC_E_ARG, "unknown model");
     memset(c, 0, sizeof(*c));
     const bool jerk = (model == BNMPC_MODEL_JERK);
     // reference src/params.py:37-61,113-122
@@ -435,6 +461,22 @@ int bnmpc_config_default(int model, bnmpc_config* c) {
     for (int i = 0; i < 4; i++) { c->tol[i] = 1e-6; c->qp_tol[i] = 1e-6; }
     c->mu0 = 1.0; c->thr0 = 0.1; c->alpha_min = 1e-8; c->lam_min = 1e-16; c->t_min = 1e-16;
     const double wx[4] = {1e2, 1e2, 1.0, 1.0};
+    if (model == BNMPC_MODEL_ATT) {
+        // our 3-D extension, numbers in the spirit of src/force_model/ocp.py:38-78 and src/params.py:45-61: position weight 100,
+        // velocity 1, attitude 10 on the vector part of the quaternion (0 on its scalar part), thrust and body rates 0.1;
+        // |p| <= 1.2, |v| <= 1, quaternion components within [-1.5, 1.5] (never active), thrust in [0.1, 2] x m g,
+        // body rates within +-6 rad/s; ERK4 for the OCP and for the plant
+        c->erk_stages = 4;
+        const double w[14] = {1e2, 1e2, 1e2, 1.0, 1.0, 1.0, 0.0, 10.0, 10.0, 10.0, 1e-1, 1e-1, 1e-1, 1e-1};
+        for (int i = 0; i < 14; i++) c->W[i] = w[i];
+        for (int i = 0; i < 10; i++) c->W_e[i] = w[i];
+        const double lb[10] = {-1.2, -1.2, -1.2, -1, -1, -1, -1.5, -1.5, -1.5, -1.5};
+        for (int i = 0; i < 10; i++) { c->lbx[i] = lb[i]; c->ubx[i] = -lb[i]; }
+        c->lbu[0] = 0.1 * GR; c->ubu[0] = 2.0 * GR;
+        for (int i = 1; i < 4; i++) { c->lbu[i] = -6.0; c->ubu[i] = 6.0; }
+        c->sim_erk_stages = 4; c->sim_substeps = 1; c->sim_dt = c->dt;
+        return 0;
+    }
     for (int i = 0; i < 4; i++) { c->W[i] = wx[i]; c->W_e[i] = wx[i]; }
     if (jerk) {
         // src/jerk_model/ocp.py:27-79, 84-92, 97-104
@@ -758,9 +800,15 @@ int bnmpc_step_for_x0(void* handle, const double* x0, const double* eps, const d
     if (int rc = stage_out_begin(h, 1, nullptr, n0 + (size_t)B * 2, 0, &dout)) return rc;
     double* dxn = dev ? x_next : dout;
     double* dup = (dev && u_plant) ? u_plant : dout + n0;
+    if (h->ops->kind == KIND_ATT) {     // no converter: the OCP input is the plant input, held for the sub-steps; u_plant = (T, wx)
+        k_sim_step_att<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.sim_erk_stages, h->cfg.sim_substeps, h->cfg.sim_dt, dx, h->gs.U0, 4, 0, dp, de, dxn);
+        CK(cudaGetLastError()); h->launches++;
+        CK(cudaMemcpy2DAsync(dup, 2 * sizeof(double), h->gs.U0, nu * sizeof(double), 2 * sizeof(double), B, cudaMemcpyDeviceToDevice, h->stream));
+    } else {
     k_convert_sim<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->ops->kind, nx, h->cfg.sim_erk_stages, h->cfg.sim_substeps, h->cfg.sim_dt, dx, h->gs.U0,
                                                            (const double*)h->gs.PAR, h->ops->np, h->ops->elem_size == 4, dp, de, dxn, dup);
     CK(cudaGetLastError()); h->launches++;
+    }
     if (!dev) {
         CK(cudaMemcpyAsync(x_next, dout, n0 * 8, out, h->stream));
         if (u_plant) CK(cudaMemcpyAsync(u_plant, dout + n0, (size_t)B * 2 * 8, out, h->stream));
@@ -790,7 +838,8 @@ int bnmpc_sim_step(void* handle, int substeps, const double* x, const double* u,
     if (use_device(h)) return BNMPC_E_CUDA;
     const int B = h->batch, nsub = substeps;
     // one staging buffer: x | u | p | eps, and a second one for the result
-    const size_t nx_ = (size_t)B * 4, nu_ = (size_t)B * nsub * 2, np_ = p_plant ? (size_t)B * 2 : 0, ne_ = eps ? (size_t)B : 0;
+    const bool att = h->ops->kind == KIND_ATT;      // 3-D model: x [B][10], u [B][substeps][4]
+    const size_t nx_ = (size_t)B * (att ? 10 : 4), nu_ = (size_t)B * nsub * (att ? 4 : 2), np_ = p_plant ? (size_t)B * 2 : 0, ne_ = eps ? (size_t)B : 0;
     const double *dx = x, *du = u, *dp = p_plant, *de = eps;
     if (on_device < 0 || on_device > BNMPC_HOST_ASYNC) return fail(BNMPC_E_ARG, "on_device must be 0, 1 or BNMPC_HOST_ASYNC");
     if (on_device != 1) {
@@ -811,7 +860,8 @@ int bnmpc_sim_step(void* handle, int substeps, const double* x, const double* u,
     }
     double* dout;
     if (int rc = stage_out_begin(h, 1, x_next, nx_, on_device == 1, &dout)) return rc;
-    k_sim_step<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.sim_erk_stages, nsub, h->cfg.sim_dt, dx, du, dp, de, dout);
+    if (att) k_sim_step_att<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.sim_erk_stages, nsub, h->cfg.sim_dt, dx, du, nsub * 4, 4, dp, de, dout);
+    else k_sim_step<<<(B + 127) / 128, 128, 0, h->stream>>>(B, h->cfg.sim_erk_stages, nsub, h->cfg.sim_dt, dx, du, dp, de, dout);
     CK(cudaGetLastError()); h->launches++;
     if (on_device == 1) return 0;
     CK(cudaMemcpyAsync(x_next, dout, nx_ * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -846,6 +896,7 @@ int bnmpc_closed_loop_run(void* handle, const bnmpc_closed_loop_args* a) {
     if (a->n_steps < 0 || a->first_step < 0) return fail(BNMPC_E_ARG, "negative step count");
     if (a->first_step + a->n_steps + h->cfg.horizon > a->ref_rows) return fail(BNMPC_E_ARG, "ref has too few rows for first_step + n_steps + N");
     if (a->noise_philox && a->noise) return fail(BNMPC_E_ARG, "noise array and noise_philox are exclusive");
+    if (h->ops->kind == KIND_ATT) return fail(BNMPC_E_UNSUPPORTED, "the 3-D attitude model has no fused closed loop: step it with bnmpc_step_for_x0");
     if (h->gs.BND) return fail(BNMPC_E_UNSUPPORTED, "per-stage bounds ('lbu'/'ubu', 'lbx'/'ubx' at stages >= 1) belong to the solve() path; the fused closed loop uses the boxes of the configuration, like the reference's follow_trajectory");
     const bool logs = a->noise || a->Xsim || a->U_plant || a->U_ctrl || a->a_log || a->status || a->qp_iter;
     if (logs && a->log_stride < a->first_step + a->n_steps) return fail(BNMPC_E_ARG, "log_stride too small");

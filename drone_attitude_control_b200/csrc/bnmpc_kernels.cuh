@@ -409,7 +409,9 @@ k_loop_ls(const __grid_constant__ Gs<T> gs, const __grid_constant__ Opts o, cons
 }
 
 // GROUPS: also instantiate the closed-loop kernel with 2 and 4 warps per instance (long horizons)
-template <class M, class T, bool GROUPS = false>
+// LOOP: the model has a fused closed loop (k_loop_step / k_loop_ls); false = the acados-style solve() surface only (the 3-D
+// attitude model: its closed loop runs through bnmpc_step_for_x0, one call per control step)
+template <class M, class T, bool GROUPS = false, bool LOOP = true>
 struct OpsImpl {
     static size_t smem_bytes(int N) { return (SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::elems(N) * sizeof(T) + 15) / 16 * 16; }
     static int tmem_cols(int N, int warps, int wpg) { return TmemPriv<M, T>::cols_needed(N, warps, 32 * wpg); }
@@ -429,16 +431,19 @@ struct OpsImpl {
     // Warps of the one CTA per SM = instances in flight per SM: bounded by registers (the launch bound), by shared memory
     // (the opt-in maximum of a block minus the static part) and by tensor memory (512 columns, one column group per warp quad).
     static cudaError_t cta_shape(int N, int* warps, int* wpg) {
-        cudaError_t e = prep(k_loop_step<M, T, 1>, 0);
-        if (e != cudaSuccess) return e;
-        if constexpr (GROUPS) {
-            e = prep(k_loop_step<M, T, 2>, 0);
+        cudaError_t e = cudaSuccess;
+        if constexpr (LOOP) {
+            e = prep(k_loop_step<M, T, 1>, 0);
             if (e != cudaSuccess) return e;
-            e = prep(k_loop_step<M, T, 4>, 0);
+            if constexpr (GROUPS) {
+                e = prep(k_loop_step<M, T, 2>, 0);
+                if (e != cudaSuccess) return e;
+                e = prep(k_loop_step<M, T, 4>, 0);
+                if (e != cudaSuccess) return e;
+            }
+            e = prep(k_loop_ls<M, T>, 0);
             if (e != cudaSuccess) return e;
         }
-        e = prep(k_loop_ls<M, T>, 0);
-        if (e != cudaSuccess) return e;
         e = prep(k_solve<M, T, false>, 0);
         if (e != cudaSuccess) return e;
         e = prep(k_solve<M, T, true>, 0);
@@ -471,6 +476,8 @@ struct OpsImpl {
     }
     // `warps` = instances per CTA, each run by a group of wpg warps
     static cudaError_t loop_step(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int wpg, int* queue, cudaStream_t st) {
+        if constexpr (!LOOP) return cudaErrorNotSupported;
+        else {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
         const int cols = tmem_cols(o.N, warps * wpg, wpg);
@@ -481,12 +488,16 @@ struct OpsImpl {
             else k_loop_step<M, T, 4><<<ctas, 128 * warps, sm, st>>>(gs_cast<T>(a), o, la, queue, cols);
         } else return cudaErrorInvalidValue;
         return cudaGetLastError();
+        }
     }
     static cudaError_t loop_ls(const GsAny& a, const Opts& o_, const LoopArgs& la, int ctas, int warps, int* queue, cudaStream_t st) {
+        if constexpr (!LOOP) return cudaErrorNotSupported;
+        else {
         Opts o = o_;
         o.smem_stride = (int)(smem_bytes(o.N) / sizeof(T));
         k_loop_ls<M, T><<<ctas, 32 * warps, smem_bytes(o.N) * warps, st>>>(gs_cast<T>(a), o, la, queue, tmem_cols(o.N, warps, 1));
         return cudaGetLastError();
+        }
     }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
@@ -494,11 +505,12 @@ struct OpsImpl {
     }
 };
 
-#define BNMPC_DEFINE_MODEL_OPS(MODEL, KIND, FN, GROUPS)                                       \
+#define BNMPC_DEFINE_MODEL_OPS(MODEL, KIND, FN, GROUPS) BNMPC_DEFINE_MODEL_OPS_(MODEL, KIND, FN, GROUPS, true)
+#define BNMPC_DEFINE_MODEL_OPS_(MODEL, KIND, FN, GROUPS, LOOP)                                \
     namespace bnmpc {                                                                         \
     const ModelOps* FN(int precision) {                                                       \
-        static const ModelOps d = OpsImpl<MODEL, double, GROUPS>::make(KIND);                  \
-        static const ModelOps f = OpsImpl<MODEL, float, GROUPS>::make(KIND);                   \
+        static const ModelOps d = OpsImpl<MODEL, double, GROUPS, LOOP>::make(KIND);            \
+        static const ModelOps f = OpsImpl<MODEL, float, GROUPS, LOOP>::make(KIND);             \
         return precision == 0 ? &d : &f;                                                      \
     }                                                                                         \
     }
@@ -507,5 +519,6 @@ const ModelOps* ops_force(int precision);
 const ModelOps* ops_jerk(int precision);
 const ModelOps* ops_force_dense(int precision);
 const ModelOps* ops_thrust(int precision);
+const ModelOps* ops_att(int precision);
 
 }  // namespace bnmpc

@@ -11,7 +11,7 @@ namespace bnmpc {
 
 // field ids of the C-ABI (include/bnmpc.h)
 enum { F_X = 0, F_U = 1, F_YREF = 2, F_LBX = 3, F_UBX = 4, F_P = 5, F_PI = 6, F_LAM = 7, F_LBU = 8, F_UBU = 9 };
-enum { KIND_FORCE = 0, KIND_JERK = 1, KIND_THRUST = 2 };
+enum { KIND_FORCE = 0, KIND_JERK = 1, KIND_THRUST = 2, KIND_ATT = 3 };
 enum { REF_BATCH_MINOR = 0, REF_SHARED = 1, REF_INSTANCE_MAJOR = 2, REF_CIRCLE = 3 };   // bnmpc_closed_loop_args.ref_shared
 
 // which block / local index holds global input g, state g

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define BNMPC_VERSION 200
+#define BNMPC_VERSION 210
 
 /* models (reference src/force_model/dynamics.py:12-47, src/jerk_model/dynamics.py:12-52).  FORCE_DENSE solves the
  * force-model OCP without exploiting the x/z block structure (the generic coupled path; in-product cross-check). */
@@ -36,6 +36,14 @@ extern "C" {
 /* NOT in the reference: the plant model (src/plant.py:27-33, u = (theta, Fd)) as controller model - a nonlinear OCP that
  * exercises the general path (sensitivities per stage and SQP iteration, several SQP iterations per solve). */
 #define BNMPC_MODEL_THRUST 3
+/* NOT in the reference: the 3-D attitude-and-total-thrust model of the north-star: states position (3),
+ * velocity (3), attitude quaternion body->world (w, x, y, z); inputs total thrust T and body rates (wx, wy, wz):
+ *   pdot = v,  vdot = (T / m) R(q) e3 - g e3,  qdot = 1/2 q (x) (0, w)       nx = 10, nu = 4, ny = 14, p = (mass, g).
+ * Box constraints on thrust and body rates (all stages) and on position / velocity (stages 1..N-1), LINEAR_LS cost, ERK4.
+ * The planar plant of src/plant.py:27-33 is its restriction to the x-z plane (theta = pitch about y, Fd = T).  It is served by
+ * the acados-style surface - set / get / solve / solve_for_x0 / step_for_x0 / sim_step (x [batch][10], u [batch][substeps][4])
+ * - and has no fused closed loop (bnmpc_closed_loop_run returns BNMPC_E_UNSUPPORTED). */
+#define BNMPC_MODEL_ATT 4
 
 #define BNMPC_FP64 0
 #define BNMPC_FP32 1
@@ -94,9 +102,9 @@ typedef struct bnmpc_config {
     int32_t threads_per_block; /* reserved (ignored): the launch shape follows from the model and the horizon - one persistent
                                CTA per SM with as many warps (= instances in flight) as the on-chip memories hold */
     double dt;              /* interval length, tf / N (src/params.py:116, src/force_model/ocp.py:93) */
-    double W[12];           /* diag of cost.W, order [x; u] (src/force_model/ocp.py:38-47) */
-    double W_e[8];          /* diag of cost.W_e */
-    double lbx[8], ubx[8];  /* state box, stages 1..N-1 (src/force_model/ocp.py:72-76) */
+    double W[16];           /* diag of cost.W, order [x; u] (src/force_model/ocp.py:38-47) */
+    double W_e[12];         /* diag of cost.W_e */
+    double lbx[12], ubx[12]; /* state box, stages 1..N-1 (src/force_model/ocp.py:72-76) */
     double lbu[4], ubu[4];  /* input box, stages 0..N-1 (src/force_model/ocp.py:62-67) */
     double tol[4];          /* NLP tolerances stat, eq, ineq, comp (acados default 1e-6) */
     double qp_tol[4];       /* QP tolerances (acados passes the NLP tolerances on to HPIPM) */

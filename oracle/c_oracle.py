@@ -8,7 +8,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, '_build', 'libnmpc_oracle.so')
 MODEL_FORCE, MODEL_JERK, MODEL_THRUST = 0, 1, 2      # THRUST: the plant model as controller model (our nonlinear extension)
-NXM, NUM, NSM = 8, 4, 12
+MODEL_ATT = 3                                        # 3-D attitude-and-total-thrust model (north-star extension)
+NXM, NUM, NSM = 12, 4, 16
 
 
 class Opts(C.Structure):
@@ -71,7 +72,7 @@ def _ip(a):
 
 
 def dims(model):
-    return (6, 2) if model == MODEL_JERK else (4, 2)
+    return (10, 4) if model == MODEL_ATT else ((6, 2) if model == MODEL_JERK else (4, 2))
 
 
 def solve_batch(o, x0, yref, p, x=None, u=None, nthreads=0):
@@ -94,6 +95,34 @@ def sim_batch(x, u, p, ns, nsub, T):
     xn = np.zeros((B, 4))
     lib().orc_sim_batch(B, ns, nsub, C.c_double(T), _dp(x), _dp(u), _dp(p), _dp(xn))
     return xn
+
+
+def sim_batch_model(model, x, u, p, ns, nsub, T):
+    """plant step of any model as its own plant (MODEL_ATT: x [B,10], u [B,nsub,4])"""
+    nx, _ = dims(model)
+    B = x.shape[0]
+    x = np.ascontiguousarray(x, float); u = np.ascontiguousarray(u, float); p = np.ascontiguousarray(p, float)
+    xn = np.zeros((B, nx))
+    lib().orc_sim_batch_model(model, B, ns, nsub, C.c_double(T), _dp(x), _dp(u), _dp(p), _dp(xn))
+    return xn
+
+
+def closed_loop_att(o, ref, x0, noise, p_ctrl, p_plant, n_steps, nthreads=0):
+    """3-D attitude model: ref [B,rows,14] or [rows,14] (shared); x0 [B,10]; noise [n_steps,B] or None; p_* [B,2]."""
+    B = x0.shape[0]
+    ref = np.ascontiguousarray(ref, float)
+    shared = ref.ndim == 2
+    rows = ref.shape[-2]
+    x0 = np.ascontiguousarray(x0, float)
+    noise = None if noise is None else np.ascontiguousarray(noise, float)
+    p_ctrl = np.ascontiguousarray(p_ctrl, float); p_plant = np.ascontiguousarray(p_plant, float)
+    out = dict(cost=np.zeros(B), Xsim=np.zeros((B, n_steps + 1, 10)), U_ctrl=np.zeros((B, n_steps, 4)),
+               status=np.zeros((B, n_steps), np.int32), qp_iter=np.zeros((B, n_steps), np.int32), sqp_iter=np.zeros((B, n_steps), np.int32))
+    rc = lib().orc_closed_loop_att(C.byref(o), B, n_steps, rows, _dp(ref), int(shared), _dp(x0), _dp(noise), _dp(p_ctrl), _dp(p_plant),
+                                   _dp(out['Xsim']), _dp(out['U_ctrl']), _dp(out['cost']), _ip(out['status']), _ip(out['qp_iter']),
+                                   _ip(out['sqp_iter']), nthreads)
+    assert rc == 0, rc
+    return out
 
 
 def closed_loop(o, ref, x0, noise, p_ctrl, p_plant, n_steps, nthreads=0, outputs=True, L=None):

@@ -24,13 +24,16 @@
 #include <pthread.h>
 #include <unistd.h>
 
-#define NXM 8
+#define NXM 12
 #define NUM 4
 #define NSM (NXM + NUM)
 
 /* MODEL_PLANT doubles as the controller model of the "thrust" OCP (inputs theta, Fd: a nonlinear OCP that is not in the
  * reference - it exercises the general SQP path: state/input dependent sensitivities, several SQP iterations) */
-enum { MODEL_FORCE = 0, MODEL_JERK = 1, MODEL_PLANT = 2 };
+enum { MODEL_FORCE = 0, MODEL_JERK = 1, MODEL_PLANT = 2, MODEL_ATT = 3 };
+/* MODEL_ATT (NOT in the reference; the north-star's 3-D attitude-and-total-thrust model): x = (p, v, q) with
+ * the attitude quaternion q = (w, x, y, z) body->world, u = (T, wx, wy, wz):  pdot = v, vdot = (T/m) R(q) e3 - g e3,
+ * qdot = 1/2 q (x) (0, w).  The planar plant of src/plant.py:27-33 is its restriction to the x-z plane. */
 
 typedef struct {
     int model;         /* MODEL_FORCE | MODEL_JERK */
@@ -60,7 +63,8 @@ typedef struct {
 #endif
 
 static void model_dims(int model, int *nx, int *nu) {
-    if (model == MODEL_JERK) { *nx = ORC_NX(6); *nu = ORC_NU(2); } else { *nx = ORC_NX(4); *nu = ORC_NU(2); }
+    if (model == MODEL_ATT) { *nx = ORC_NX(10); *nu = ORC_NU(4); }
+    else if (model == MODEL_JERK) { *nx = ORC_NX(6); *nu = ORC_NU(2); } else { *nx = ORC_NX(4); *nu = ORC_NU(2); }
 }
 
 /* xdot = f(x,u,p), p = (mass, g) */
@@ -69,6 +73,13 @@ static void model_f(int model, const double *x, const double *u, const double *p
     switch (model) {
     case MODEL_FORCE: xd[0] = x[2]; xd[1] = x[3]; xd[2] = u[0] / m; xd[3] = u[1] / m - g; break;
     case MODEL_JERK:  xd[0] = x[2]; xd[1] = x[3]; xd[2] = x[4]; xd[3] = x[5] - g; xd[4] = u[0]; xd[5] = u[1]; break;
+    case MODEL_ATT: {
+        const double qw = x[6], qx = x[7], qy = x[8], qz = x[9], a = u[0] / m, wx = u[1], wy = u[2], wz = u[3];
+        xd[0] = x[3]; xd[1] = x[4]; xd[2] = x[5];
+        xd[3] = 2.0 * (qx * qz + qw * qy) * a; xd[4] = 2.0 * (qy * qz - qw * qx) * a; xd[5] = (1.0 - 2.0 * (qx * qx + qy * qy)) * a - g;
+        xd[6] = 0.5 * (-qx * wx - qy * wy - qz * wz); xd[7] = 0.5 * (qw * wx + qy * wz - qz * wy);
+        xd[8] = 0.5 * (qw * wy - qx * wz + qz * wx);  xd[9] = 0.5 * (qw * wz + qx * wy - qy * wx);
+    } break;
     default:          xd[0] = x[2]; xd[1] = x[3]; xd[2] = u[1] * sin(u[0]) / m; xd[3] = u[1] * cos(u[0]) / m - g; break;
     }
 }
@@ -82,6 +93,26 @@ static void model_jac(int model, const double *x, const double *u, const double 
     switch (model) {
     case MODEL_FORCE: fx[0 * 4 + 2] = 1; fx[1 * 4 + 3] = 1; fu[2 * 2 + 0] = 1 / m; fu[3 * 2 + 1] = 1 / m; break;
     case MODEL_JERK:  fx[0 * 6 + 2] = 1; fx[1 * 6 + 3] = 1; fx[2 * 6 + 4] = 1; fx[3 * 6 + 5] = 1; fu[4 * 2 + 0] = 1; fu[5 * 2 + 1] = 1; break;
+    case MODEL_ATT: {
+        const double qw = x[6], qx = x[7], qy = x[8], qz = x[9], a = u[0] / m, wx = u[1], wy = u[2], wz = u[3];
+#define FX(r, c) fx[(r) * 10 + (c)]
+#define FU(r, c) fu[(r) * 4 + (c)]
+        FX(0, 3) = 1; FX(1, 4) = 1; FX(2, 5) = 1;
+        FX(3, 6) = 2 * qy * a;  FX(3, 7) = 2 * qz * a;  FX(3, 8) = 2 * qw * a; FX(3, 9) = 2 * qx * a;
+        FX(4, 6) = -2 * qx * a; FX(4, 7) = -2 * qw * a; FX(4, 8) = 2 * qz * a; FX(4, 9) = 2 * qy * a;
+        FX(5, 7) = -4 * qx * a; FX(5, 8) = -4 * qy * a;
+        FX(6, 7) = -0.5 * wx; FX(6, 8) = -0.5 * wy; FX(6, 9) = -0.5 * wz;
+        FX(7, 6) = 0.5 * wx;  FX(7, 8) = 0.5 * wz;  FX(7, 9) = -0.5 * wy;
+        FX(8, 6) = 0.5 * wy;  FX(8, 7) = -0.5 * wz; FX(8, 9) = 0.5 * wx;
+        FX(9, 6) = 0.5 * wz;  FX(9, 7) = 0.5 * wy;  FX(9, 8) = -0.5 * wx;
+        FU(3, 0) = 2.0 * (qx * qz + qw * qy) / m; FU(4, 0) = 2.0 * (qy * qz - qw * qx) / m; FU(5, 0) = (1.0 - 2.0 * (qx * qx + qy * qy)) / m;
+        FU(6, 1) = -0.5 * qx; FU(6, 2) = -0.5 * qy; FU(6, 3) = -0.5 * qz;
+        FU(7, 1) = 0.5 * qw;  FU(7, 2) = -0.5 * qz; FU(7, 3) = 0.5 * qy;
+        FU(8, 1) = 0.5 * qz;  FU(8, 2) = 0.5 * qw;  FU(8, 3) = -0.5 * qx;
+        FU(9, 1) = -0.5 * qy; FU(9, 2) = 0.5 * qx;  FU(9, 3) = 0.5 * qw;
+#undef FX
+#undef FU
+    } break;
     default:
         fx[0 * 4 + 2] = 1; fx[1 * 4 + 3] = 1;
         fu[2 * 2 + 0] = u[1] * cos(u[0]) / m;  fu[2 * 2 + 1] = sin(u[0]) / m;
@@ -640,7 +671,16 @@ void orc_default_opts(int model, orc_opts *o) {
     for (int i = 0; i < 4; i++) { o->tol[i] = 1e-6; o->qp_tol[i] = 1e-6; }
     o->mu0 = 1.0; o->thr0 = 0.1; o->alpha_min = 1e-8; o->lam_min = 1e-16; o->t_min = 1e-16;
     const double wx[4] = {1e2, 1e2, 1.0, 1.0};
-    if (model == MODEL_PLANT) {   /* thrust OCP (our extension): same state cost and boxes as the force model, u = (theta, Fd) */
+    if (model == MODEL_ATT) {     /* 3-D attitude OCP (our extension; same numbers as bnmpc_config_default) */
+        o->erk_stages = 4;
+        const double w[14] = {1e2, 1e2, 1e2, 1.0, 1.0, 1.0, 0.0, 10.0, 10.0, 10.0, 1e-1, 1e-1, 1e-1, 1e-1};
+        for (int i = 0; i < 14; i++) o->w[i] = w[i];
+        for (int i = 0; i < 10; i++) o->w_e[i] = w[i];
+        const double lb[10] = {-1.2, -1.2, -1.2, -1, -1, -1, -1.5, -1.5, -1.5, -1.5};
+        for (int i = 0; i < 10; i++) { o->lbx[i] = lb[i]; o->ubx[i] = -lb[i]; }
+        o->lbu[0] = 0.1 * GR; o->ubu[0] = 2.0 * GR;
+        for (int i = 1; i < 4; i++) { o->lbu[i] = -6.0; o->ubu[i] = 6.0; }
+    } else if (model == MODEL_PLANT) {   /* thrust OCP (our extension): same state cost and boxes as the force model, u = (theta, Fd) */
         o->erk_stages = 4;
         for (int i = 0; i < 4; i++) { o->w[i] = wx[i]; o->w_e[i] = wx[i]; }
         o->w[4] = o->w[5] = 1e-1;
@@ -741,6 +781,17 @@ int orc_sim_batch(int B, int ns, int nsub, double T, const double *x, const doub
     return 0;
 }
 
+/* the same for any model as its own plant (MODEL_ATT: x [B][10], u [B][nsub][4]) */
+int orc_sim_batch_model(int model, int B, int ns, int nsub, double T, const double *x, const double *u, const double *p, double *xn) {
+    int nx, nu; model_dims(model, &nx, &nu);
+    for (int i = 0; i < B; i++) {
+        double xi[NXM]; memcpy(xi, x + (size_t)i * nx, sizeof(double) * nx);
+        for (int j = 0; j < nsub; j++) erk_step(model, xi, u + ((size_t)i * nsub + j) * nu, p + (size_t)i * 2, T, ns, 1, xi, NULL);
+        memcpy(xn + (size_t)i * nx, xi, sizeof(double) * nx);
+    }
+    return 0;
+}
+
 typedef struct {
     const orc_opts *o; int B, n_steps, rows, ref_shared; const double *ref, *x0, *noise, *p_ctrl, *p_plant;
     double *Xsim, *U_plant, *U_ctrl, *a_log, *cost; int *status, *qp_iter;
@@ -815,5 +866,56 @@ int orc_closed_loop(const orc_opts *o, int B, int n_steps, int rows, const doubl
     if (rows < n_steps + o->N) return -1;
     cl_ctx c = {o, B, n_steps, rows, ref_shared, ref, x0, noise, p_ctrl, p_plant, Xsim, U_plant, U_ctrl, a_log, cost, status, qp_iter};
     parallel_for(B, nthreads, nx, nu, o->N, closed_loop_one, &c);
+    return 0;
+}
+
+/* Closed loop of the 3-D attitude model (follow_trajectory with the controller model as its own plant, the shape of
+ * src/force_model/controller.py:25-54): per step yref window from ref, x0 embedding, solve, u0 held over one ERK4 plant step of
+ * length dt with the PLANT parameters, eps added to position and velocity.
+ *   ref [B][rows][14] = [x (10); u (4)] per row (or one shared table); x0 [B][10]; noise [n_steps][B] or NULL; p_* [B][2]
+ *   outputs (any may be NULL): Xsim [B][n_steps+1][10], U_ctrl [B][n_steps][4], cost [B], status / qp_iter / sqp_iter [B][n_steps] */
+typedef struct {
+    const orc_opts *o; int B, n_steps, rows, ref_shared; const double *ref, *x0, *noise, *p_ctrl, *p_plant;
+    double *Xsim, *U_ctrl, *cost; int *status, *qp_iter, *sqp_iter;
+} cla_ctx;
+
+static void closed_loop_att_one(void *vc, inst_t *s, double *yref, int i) {
+    cla_ctx *c = (cla_ctx *)vc;
+    const orc_opts *o = c->o;
+    const int nx = s->nx, nu = s->nu, N = s->N, ny = nx + nu, n_steps = c->n_steps, B = c->B;
+    const double *rt = c->ref + (c->ref_shared ? 0 : (size_t)i * c->rows * ny);
+    const double *pc = c->p_ctrl + (size_t)i * 2, *pp = c->p_plant + (size_t)i * 2;
+    memset(s->x, 0, sizeof(double) * (N + 1) * nx); memset(s->u, 0, sizeof(double) * N * nu); s->have_mult = 0;
+    for (int k = 0; k <= N; k++) s->x[k * nx + 6] = 1.0;      /* start iterate: identity attitude, hover thrust */
+    for (int k = 0; k < N; k++) s->u[k * nu] = pc[0] * pc[1];
+    double xs[NXM]; memcpy(xs, c->x0 + (size_t)i * nx, sizeof(double) * nx);
+    double csum = 0;
+    if (c->Xsim) memcpy(c->Xsim + (size_t)i * (n_steps + 1) * nx, xs, sizeof(double) * nx);
+    for (int st = 0; st < n_steps; st++) {
+        for (int k = 0; k < N; k++) for (int j = 0; j < ny; j++) yref[k * ny + j] = rt[(size_t)(st + k) * ny + j];
+        for (int j = 0; j < nx; j++) yref[N * ny + j] = rt[(size_t)(st + N) * ny + j];
+        int si_, qi_;
+        int stt = sqp_solve(o, s, xs, yref, pc, &si_, &qi_);
+        if (c->status) c->status[(size_t)i * n_steps + st] = stt;
+        if (c->qp_iter) c->qp_iter[(size_t)i * n_steps + st] = qi_;
+        if (c->sqp_iter) c->sqp_iter[(size_t)i * n_steps + st] = si_;
+        for (int j = 0; j < 6; j++) { double d = s->x[j] - rt[(size_t)st * ny + j]; csum += (j < 3 ? 1e2 : 1.0) * d * d; }
+        double xn[NXM];
+        erk_step(MODEL_ATT, xs, s->u, pp, o->dt, 4, 1, xn, NULL);
+        const double eps = c->noise ? c->noise[(size_t)st * B + i] : 0.0;
+        for (int j = 0; j < nx; j++) xs[j] = xn[j] + (j < 6 ? eps : 0.0);
+        if (c->U_ctrl) memcpy(c->U_ctrl + ((size_t)i * n_steps + st) * nu, s->u, sizeof(double) * nu);
+        if (c->Xsim) memcpy(c->Xsim + ((size_t)i * (n_steps + 1) + st + 1) * nx, xs, sizeof(double) * nx);
+    }
+    if (c->cost) c->cost[i] = csum;
+}
+
+int orc_closed_loop_att(const orc_opts *o, int B, int n_steps, int rows, const double *ref, int ref_shared, const double *x0,
+                        const double *noise, const double *p_ctrl, const double *p_plant, double *Xsim, double *U_ctrl, double *cost,
+                        int *status, int *qp_iter, int *sqp_iter, int nthreads) {
+    int nx, nu; model_dims(o->model, &nx, &nu);
+    if (o->model != MODEL_ATT || rows < n_steps + o->N) return -1;
+    cla_ctx c = {o, B, n_steps, rows, ref_shared, ref, x0, noise, p_ctrl, p_plant, Xsim, U_ctrl, cost, status, qp_iter, sqp_iter};
+    parallel_for(B, nthreads, nx, nu, o->N, closed_loop_att_one, &c);
     return 0;
 }

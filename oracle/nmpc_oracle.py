@@ -103,6 +103,42 @@ def jac_plant(x, u, p):
     return fx, fu
 
 
+def f_att(x, u, p):
+    """NOT in the reference: the 3-D attitude-and-total-thrust model of the north-star.  x = (p, v, q) with
+    q = (w, x, y, z) the attitude quaternion body->world, u = (T, wx, wy, wz):  pdot = v, vdot = (T/m) R(q) e3 - g e3,
+    qdot = 1/2 q (x) (0, w).  The planar plant (src/plant.py:27-33) is its restriction to the x-z plane."""
+    m, g = p
+    qw, qx, qy, qz = x[6:10]
+    a = u[0] / m
+    wx, wy, wz = u[1:4]
+    return np.array([x[3], x[4], x[5],
+                     2.0 * (qx * qz + qw * qy) * a, 2.0 * (qy * qz - qw * qx) * a, (1.0 - 2.0 * (qx * qx + qy * qy)) * a - g,
+                     0.5 * (-qx * wx - qy * wy - qz * wz), 0.5 * (qw * wx + qy * wz - qz * wy),
+                     0.5 * (qw * wy - qx * wz + qz * wx), 0.5 * (qw * wz + qx * wy - qy * wx)])
+
+
+def jac_att(x, u, p):
+    m, g = p
+    qw, qx, qy, qz = x[6:10]
+    a = u[0] / m
+    wx, wy, wz = u[1:4]
+    fx = np.zeros((10, 10)); fu = np.zeros((10, 4))
+    fx[0, 3] = fx[1, 4] = fx[2, 5] = 1.0
+    fx[3, 6:10] = [2 * qy * a, 2 * qz * a, 2 * qw * a, 2 * qx * a]
+    fx[4, 6:10] = [-2 * qx * a, -2 * qw * a, 2 * qz * a, 2 * qy * a]
+    fx[5, 7] = -4 * qx * a; fx[5, 8] = -4 * qy * a
+    fx[6, 7:10] = [-0.5 * wx, -0.5 * wy, -0.5 * wz]
+    fx[7, 6] = 0.5 * wx; fx[7, 8] = 0.5 * wz; fx[7, 9] = -0.5 * wy
+    fx[8, 6] = 0.5 * wy; fx[8, 7] = -0.5 * wz; fx[8, 9] = 0.5 * wx
+    fx[9, 6] = 0.5 * wz; fx[9, 7] = 0.5 * wy; fx[9, 8] = -0.5 * wx
+    fu[3, 0] = 2.0 * (qx * qz + qw * qy) / m; fu[4, 0] = 2.0 * (qy * qz - qw * qx) / m; fu[5, 0] = (1.0 - 2.0 * (qx * qx + qy * qy)) / m
+    fu[6, 1:4] = [-0.5 * qx, -0.5 * qy, -0.5 * qz]
+    fu[7, 1:4] = [0.5 * qw, -0.5 * qz, 0.5 * qy]
+    fu[8, 1:4] = [0.5 * qz, 0.5 * qw, -0.5 * qx]
+    fu[9, 1:4] = [-0.5 * qy, 0.5 * qx, 0.5 * qw]
+    return fx, fu
+
+
 # Butcher tableaus of acados sim_erk for num_stages = 1, 2, 3, 4 (explicit Euler, midpoint, Kutta-3, classic RK4)
 _ERK = {
     1: (np.array([[0.0]]), np.array([1.0])),
@@ -250,6 +286,17 @@ def thrust_ocp(N=N_HORIZON, **kw):
                    w=np.array([1e2, 1e2, 1.0, 1.0, 1e-1, 1e-1]), w_e=np.array([1e2, 1e2, 1.0, 1.0]),
                    lbx=np.array([-P_LIM, -P_LIM, -V_LIM, -V_LIM]), ubx=np.array([P_LIM, P_LIM, V_LIM, V_LIM]),
                    lbu=np.array([-1.0, 0.05]), ubu=np.array([1.0, 0.6]), N=N, **kw)
+
+
+def att_ocp(N=N_HORIZON, **kw):
+    """NOT in the reference: the OCP of the 3-D attitude model (same numbers as bnmpc_config_default(BNMPC_MODEL_ATT)):
+    position weight 100, velocity 1, quaternion vector part 10, inputs 0.1; |p| <= 1.2, |v| <= 1, thrust within [0.1, 2] m g,
+    body rates within +-6 rad/s; ERK4."""
+    GR = MASS * GRAVITY_ACC
+    w = np.array([1e2, 1e2, 1e2, 1.0, 1.0, 1.0, 0.0, 10.0, 10.0, 10.0, 1e-1, 1e-1, 1e-1, 1e-1])
+    ub = np.array([P_LIM, P_LIM, P_LIM, V_LIM, V_LIM, V_LIM, 1.5, 1.5, 1.5, 1.5])
+    return OcpSpec('att', 10, 4, f_att, jac_att, 4, w=w, w_e=w[:10].copy(), lbx=-ub, ubx=ub,
+                   lbu=np.array([0.1 * GR, -6.0, -6.0, -6.0]), ubu=np.array([2.0 * GR, 6.0, 6.0, 6.0]), N=N, **kw)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -12,7 +12,7 @@ _SRC = [os.path.join(_HERE, 'hostsim.cpp')] + [
     os.path.join(_HERE, '..', '..', 'drone_attitude_control_b200', 'csrc', f)
     for f in ('bnmpc_core.cuh', 'bnmpc_loop.cuh', 'bnmpc_lockstep.cuh', 'generated/models_gen.cuh')]
 
-MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_JERK_DENSE, MODEL_THRUST = 0, 1, 2, 3, 4
+MODEL_FORCE, MODEL_JERK, MODEL_FORCE_DENSE, MODEL_JERK_DENSE, MODEL_THRUST, MODEL_ATT = 0, 1, 2, 3, 4, 5
 FP64, FP32 = 0, 1
 
 
@@ -20,7 +20,7 @@ class Opts(C.Structure):
     _fields_ = [('N', C.c_int), ('erk_stages', C.c_int), ('sqp_max_iter', C.c_int), ('qp_max_iter', C.c_int), ('rti', C.c_int),
                 ('sim_erk_stages', C.c_int), ('sim_substeps', C.c_int), ('smem_stride', C.c_int), ('order', C.c_void_p),
                 ('dt', C.c_double), ('sim_dt', C.c_double),
-                ('W', C.c_double * 12), ('W_e', C.c_double * 8), ('lbx', C.c_double * 8), ('ubx', C.c_double * 8),
+                ('W', C.c_double * 16), ('W_e', C.c_double * 12), ('lbx', C.c_double * 12), ('ubx', C.c_double * 12),
                 ('lbu', C.c_double * 4), ('ubu', C.c_double * 4), ('tol', C.c_double * 4), ('qp_tol', C.c_double * 4),
                 ('mu0', C.c_double), ('thr0', C.c_double), ('alpha_min', C.c_double), ('lam_min', C.c_double), ('t_min', C.c_double)]
 
@@ -51,9 +51,9 @@ def opts_from_oracle(oo):
     o.N, o.erk_stages, o.sqp_max_iter, o.qp_max_iter, o.rti = oo.N, oo.erk_stages, oo.sqp_max_iter, oo.qp_max_iter, oo.rti
     o.sim_erk_stages, o.sim_substeps = (1, 10) if jerk else (4, 1)
     o.dt, o.sim_dt = oo.dt, (1.0 / 500 if jerk else oo.dt)
-    for i in range(12):
+    for i in range(16):
         o.W[i] = oo.w[i]
-    for i in range(8):
+    for i in range(12):
         o.W_e[i], o.lbx[i], o.ubx[i] = oo.w_e[i], oo.lbx[i], oo.ubx[i]
     for i in range(4):
         o.lbu[i], o.ubu[i], o.tol[i], o.qp_tol[i] = oo.lbu[i], oo.ubu[i], oo.tol[i], oo.qp_tol[i]
@@ -71,11 +71,11 @@ def _ip(a):
 
 def solve_batch(model, prec, o, x0, yref, p, x=None, u=None, bnd=None):
     """bnd: per-stage bounds [B, N, 2, nu + nx] (lower / upper, per stage [u; x]) or None = the boxes of `o`"""
-    nx = 6 if model in (1, 3) else 4
+    nx, nu = (10, 4) if model == MODEL_ATT else ((6, 2) if model in (1, 3) else (4, 2))
     B, N = x0.shape[0], o.N
     x0 = np.ascontiguousarray(x0, float); yref = np.ascontiguousarray(yref, float); p = np.ascontiguousarray(p, float)
     x = np.zeros((B, N + 1, nx)) if x is None else np.array(x, float, order='C')
-    u = np.zeros((B, N, 2)) if u is None else np.array(u, float, order='C')
+    u = np.zeros((B, N, nu)) if u is None else np.array(u, float, order='C')
     pi = np.zeros((B, N, nx))
     st = np.zeros(B, np.int32); si = np.zeros(B, np.int32); qi = np.zeros(B, np.int32)
     bnd = None if bnd is None else np.ascontiguousarray(bnd, float)

@@ -205,6 +205,9 @@ void hs_circle_table(int B, int rows, int n, const double* prm, double* out) {
 // AoS in/out like the C oracle's orc_solve_batch: x [B][N+1][NX], u [B][N][NU] (start iterate in, solution out)
 int hs_solve_batch(int model, int prec, const Opts* o, int B, const double* x0, const double* yref, const double* p, double* x,
                    double* u, double* pi, int* status, int* sqp_iter, int* qp_iter, const double* bnd) {
+    // the 3-D attitude model has the solve() surface only (no fused closed loop)
+    if (model == 5) return prec ? solve_batch_t<Model_att, float>(o, B, x0, yref, p, x, u, pi, status, sqp_iter, qp_iter, bnd)
+                                : solve_batch_t<Model_att, double>(o, B, x0, yref, p, x, u, pi, status, sqp_iter, qp_iter, bnd);
     DISPATCH(solve_batch_t, model, prec, o, B, x0, yref, p, x, u, pi, status, sqp_iter, qp_iter, bnd)
 }
 // batch-minor in/out exactly like bnmpc_closed_loop_* (x0 [4][B], p_* [2][B], ref shared [rows][8] or [rows][8][B], logs [steps][dim][B])

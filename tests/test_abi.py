@@ -24,7 +24,7 @@ def test_every_declared_symbol_is_exported():
     assert len(names) >= 20
     for n in names:
         assert hasattr(L, n), f'{n} declared in include/bnmpc.h but not exported by libbnmpc.so'
-    assert L.bnmpc_version() == 200
+    assert L.bnmpc_version() == 210
 
 
 def test_struct_sizes_and_defaults_match_reference_constants():
