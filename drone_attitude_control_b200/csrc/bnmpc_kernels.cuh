@@ -226,7 +226,7 @@ __device__ __forceinline__ int warp_smem_off(int stride_elems, int group_lanes =
 // launch bound of a model: instances that fit shared memory at the reference horizon, whole warp quads, <= BNMPC_MAX_WARPS
 template <class M, class T>
 struct LaunchShape {
-    static constexpr size_t REF_BYTES = ((size_t)SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::STRIDE * (31 * M::NBLK) + M::NX) * sizeof(T);
+    static constexpr size_t REF_BYTES = SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::elems(30) * sizeof(T);
     static constexpr int FIT = (int)((227 * 1024 - 1024) / REF_BYTES);
     static constexpr int MAX_WARPS = FIT >= BNMPC_MAX_WARPS ? BNMPC_MAX_WARPS : (FIT >= 4 ? FIT / 4 * 4 : (FIT >= 1 ? FIT : 1));
 };

@@ -29,7 +29,8 @@ def build(force=False):
     newest = max(os.path.getmtime(f) for f in _SRC)
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < newest:
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
-        subprocess.check_call(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-pthread', '-mfma', '-o', _SO, _SRC[0]])
+        extra = ['-DHS_ONLY_ATT'] if os.environ.get('BNMPC_HOSTSIM_ATT_ONLY') else []
+        subprocess.check_call(['g++', '-O1', '-std=c++17', '-fPIC', '-shared', '-pthread', '-mfma', '-o', _SO, _SRC[0]] + extra)
     return _SO
 
 

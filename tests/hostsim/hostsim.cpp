@@ -180,6 +180,9 @@ static int closed_loop_ls_t(const Opts* o, int kind, int B, int n_steps, int chu
     return 0;
 }
 
+#ifdef HS_ONLY_ATT      // quick build while working on the 3-D model: only its instantiations
+#define DISPATCH(fn, model, prec, ...) return -2;
+#else
 #define DISPATCH(fn, model, prec, ...)                                                     \
     switch ((model) * 2 + (prec)) {                                                        \
     case 0: return fn<Model_force, double>(__VA_ARGS__);                                   \
@@ -194,6 +197,7 @@ static int closed_loop_ls_t(const Opts* o, int kind, int B, int n_steps, int chu
     case 9: return fn<Model_plant, float>(__VA_ARGS__);                                    \
     }                                                                                      \
     return -2;
+#endif
 
 extern "C" {
 int hs_sizeof_opts(void) { return (int)sizeof(Opts); }
