@@ -503,7 +503,74 @@ def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):
     out['config4_force_262144_mass_perturbed_sharded'] = dict(one('force', 262144, 30, 'fp64', 10, 3, 0.05, True), scaling='strong')
     for N in (20, 50, 100):
         out[f'config5_force_65536_N{N}'] = one('force', 65536, N, 'fp64', 4 if N > 30 else 8, 2, 0.0, False)
+    out['north_star_att_3d_nx10_nu4'] = att_extra(args, dev, local, rank, world, barrier, allmax)
     return out
+
+
+def att_extra(args, dev, local, rank, world, barrier, allmax, per_rank=4736, steps=6, warm=4):
+    """The 3-D attitude-and-total-thrust OCP of the north-star (nx 10, nu 4; not in the reference): closed loop of `per_rank`
+    drones per GPU on per-instance helix references with a 5 % plant-mass perturbation, device-resident, one
+    bnmpc_step_for_x0 per control step (solve kernel + plant kernel); SQP to tolerance.  With --skip-cpu unset, rank 0 also
+    times the C restatement (oracle/, kind "port") on a bounded sample of the same instances on all host cores."""
+    import torch
+    from drone_attitude_control_b200.attitude_model import follow_trajectory_batched, helix_table
+    from drone_attitude_control_b200.sharding import instance_inputs
+    lo, hi = rank * per_rank, (rank + 1) * per_rank
+    inp = instance_inputs(lo, hi, 0, seed=SEED, mass_sigma=0.05, with_noise=False)
+    b = hi - lo
+    c3 = torch.stack([inp['center'][:, 0], torch.zeros(b, dtype=torch.float64), inp['center'][:, 1]], 1)
+    rows = warm + steps + 30
+    ref = helix_table(inp['radius'] * 0.9, c3, inp['phase'], 0.2 * inp['radius'], rows, device=dev)
+    x0 = ref[:, 0, :10].clone()
+    x0[:, :4] += inp['dx0'].to(dev).T
+    pp = torch.stack([0.03277 * inp['mass_scale'], torch.full((b,), 9.81, dtype=torch.float64)], 1).to(dev)
+    state = {}
+
+    def run(first, n, x):
+        r = follow_trajectory_batched(ref[:, first:], x, n, p_plant=pp, device=local, log=True, solver=state.get('solver'))
+        state['solver'] = r['solver']
+        return r
+    r0 = run(0, warm, x0)                                     # warm-up: the cold-start solves
+    torch.cuda.synchronize(); barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); r1 = run(warm, steps, r0['Xsim'][:, -1].contiguous()); e1.record()
+    barrier()
+    ms = allmax(e0.elapsed_time(e1))
+    st = torch.tensor([float((r1['status'] != 0).sum()), float(r1['qp_iter'].sum()), float(r1['sqp_iter'].sum()), float(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(st)
+    tot = int(st[3])
+    out = {'model': 'att', 'instances_total': tot, 'horizon': 30, 'precision': 'fp64', 'steps': steps, 'warmup': warm, 'ms': ms,
+           'value': tot * steps / (ms * 1e-3), 'unit': UNIT, 'failed_steps': int(st[0]), 'qp_iter_mean': float(st[1]) / (tot * steps),
+           'sqp_iter_mean': float(st[2]) / (tot * steps), 'launches_per_step': 2,
+           'path': 'bnmpc_set_yref_all + bnmpc_step_for_x0 per control step, device buffers'}
+    fl = flops_per_solve(1, 10, 4, 30, 4, out['qp_iter_mean'], out['sqp_iter_mean'] + 1.0) * tot * steps
+    out['achieved_tflops'] = fl / (ms * 1e-3) * 1e-12
+    tf = C_peak(local)
+    out['roofline_frac'] = out['achieved_tflops'] / tf if tf else None
+    if not args.skip_cpu and rank == 0:
+        import time
+        from oracle import c_oracle as co
+        ns = min(b, 8 * max(1, co.lib().orc_num_cores()))
+        oc = co.default_opts(co.MODEL_ATT)
+        xs = r0['Xsim'][:ns, -1].cpu().numpy()
+        it = np.zeros((ns, 31, 10)); it[:, :, 6] = 1.0
+        t0 = time.perf_counter()
+        w = co.closed_loop_att(oc, ref[:ns, warm:].cpu().numpy(), xs, None, np.tile([0.03277, 9.81], (ns, 1)), pp[:ns].cpu().numpy(), steps)
+        dt_ = time.perf_counter() - t0
+        out['cpu_baseline'] = {'value': ns * steps / dt_, 'unit': UNIT, 'cores': int(co.lib().orc_num_cores()), 'kind': 'port',
+                               'sample': f'{ns} of the same instances x {steps} steps from the same plant states (cold iterate), all host cores',
+                               'qp_iter_mean': float(w['qp_iter'].mean())}
+    return out
+
+
+def C_peak(local):
+    import ctypes as C
+    from drone_attitude_control_b200 import _lib
+    tf = C.c_double()
+    _lib.check(_lib.lib().bnmpc_measure_fma_peak(local, _lib.FP64, C.byref(tf)))
+    return tf.value
 
 
 def run_reference(args):

@@ -40,6 +40,27 @@ def gen_helix_traj(n_steps=None, n_horizon=None, center=(0.0, 0.0, 0.0), radius=
     return np.vstack((x, x[:nh])), np.vstack((u, u[:nh]))
 
 
+def helix_table(radius, center, phase, y_amp, rows, device=None, dt=None, mass=None, g=None):
+    """Batched reference tables on the device (torch): [B, rows, 14] = [xref (10) | uref (4)] per row, the helix of
+    gen_helix_traj sampled at the control rate (row i at t = i dt) for per-instance radius [B], centre [B, 3], phase [B],
+    y_amp [B]."""
+    import torch
+    dt = p.dt if dt is None else dt
+    f64 = dict(dtype=torch.float64, device=device)
+    radius, center, phase, y_amp = (torch.as_tensor(a, **f64) for a in (radius, center, phase, y_amp))
+    t = torch.arange(rows, **f64) * dt
+    om = 2 * np.pi / p.T
+    a = om * t[None, :] + phase[:, None]
+    B = radius.shape[0]
+    out = torch.zeros((B, rows, NX + NU), **f64)
+    R, Y = radius[:, None], y_amp[:, None]
+    out[:, :, 0] = center[:, 0:1] + R * torch.cos(a); out[:, :, 1] = center[:, 1:2] + Y * torch.sin(2 * a); out[:, :, 2] = center[:, 2:3] + R * torch.sin(a)
+    out[:, :, 3] = -R * om * torch.sin(a); out[:, :, 4] = 2 * om * Y * torch.cos(2 * a); out[:, :, 5] = R * om * torch.cos(a)
+    out[:, :, 6] = 1.0
+    out[:, :, 10] = float(hover_input(mass, g)[0])
+    return out
+
+
 class Converter:
     """The OCP input already is the plant input (total thrust, body rates): convert() is the identity (the counterpart of
     reference src/force_model/dynamics.py:54-79, which maps (Fx, Fz) to (theta, Fd))."""
@@ -132,7 +153,7 @@ def follow_trajectory(xref, uref, x0, noise, verbose=False, device=0, n_steps=No
 
 
 def follow_trajectory_batched(ref, x0, n_steps, noise=None, p_ctrl=None, p_plant=None, device=0, precision='fp64', log=True,
-                              **overrides):
+                              solver=None, **overrides):
     """Closed loop of `batch` drones, device-resident: per control step the yref windows are gathered on the device and ONE
     bnmpc_step_for_x0 call does the x0 embedding, solve(), get(0, 'u') and the plant step with the noise draw.
     ref [B, rows, 14] or [rows, 14] (shared) = [xref (10) | uref (4)] per row, rows >= n_steps + N; x0 [B, 10];
@@ -143,21 +164,22 @@ def follow_trajectory_batched(ref, x0, n_steps, noise=None, p_ctrl=None, p_plant
     T = lambda a: None if a is None else torch.as_tensor(a, dtype=torch.float64).to(dev).contiguous()
     ref, x0, noise, p_ctrl, p_plant = T(ref), T(x0), T(noise), T(p_ctrl), T(p_plant)
     B = x0.shape[0]
-    s = BatchedAcadosOcpSolver('att', batch=B, device=device, precision=precision, N_horizon=overrides.pop('N_horizon', p.N_horizon),
-                               numpy_io=False, **overrides)
+    fresh = solver is None            # (a solver passed in continues from its iterate: a second leg of the same loop)
+    s = solver if solver is not None else BatchedAcadosOcpSolver('att', batch=B, device=device, precision=precision,
+                                                                 N_horizon=overrides.pop('N_horizon', p.N_horizon), numpy_io=False, **overrides)
     N, ny = s.N, NX + NU
     if ref.dim() == 2:
         ref = ref[None].expand(B, -1, -1)
     assert ref.shape[1] >= n_steps + N and ref.shape[2] == ny
-    if p_ctrl is not None:
+    if p_ctrl is not None and fresh:
         s.set(0, 'p', p_ctrl)
     mass = p_ctrl[:, 0] if p_ctrl is not None else torch.full((B,), dd.MASS, dtype=torch.float64, device=dev)
     grav = p_ctrl[:, 1] if p_ctrl is not None else torch.full((B,), dd.GRAVITY_ACC, dtype=torch.float64, device=dev)
     xg = torch.zeros((B, NX), dtype=torch.float64, device=dev); xg[:, 6] = 1.0
     ug = torch.zeros((B, NU), dtype=torch.float64, device=dev); ug[:, 0] = mass * grav
-    for k in range(N + 1):
+    for k in range(N + 1 if fresh else 0):
         s.set(k, 'x', xg)
-    for k in range(N):
+    for k in range(N if fresh else 0):
         s.set(k, 'u', ug)
     x = x0.clone()
     xn = torch.empty_like(x)

@@ -164,6 +164,16 @@ def gen_model(name, xs, us, ps, f, force_single_block=False):
         L.append('        constexpr bool tab[%d][%d] = {%s};' % (nxb, nc, rows))
         L.append('        return tab[r][c];')
         L.append('    }')
+    # structural zeros of the continuous-time Jacobians of a block (entries that are identically zero in every block): the
+    # sensitivity propagation of a large block skips those products (erk_step)
+    jx_zero = [[all(Jx[cx[r], cx[c]] == 0 for cx, _ in comps) for c in range(nxb)] for r in range(nxb)]
+    ju_zero = [[all(Ju[cx[r], cu[c]] == 0 for cx, cu in comps) for c in range(nub)] for r in range(nxb)]
+    for nm, tab, nc in (('jx_zero', jx_zero, nxb), ('ju_zero', ju_zero, max(nub, 1))):
+        rows = ', '.join('{' + ', '.join('true' if v else 'false' for v in row) + '}' for row in tab)
+        L.append('    __host__ __device__ static constexpr bool %s(int r, int c) {' % nm)
+        L.append('        constexpr bool tab[%d][%d] = {%s};' % (nxb, nc, rows))
+        L.append('        return tab[r][c];')
+        L.append('    }')
     for nm, idx in (('xg', 0), ('ug', 1)):
         n_loc = nxb if idx == 0 else nub
         rows = ', '.join('{' + ', '.join(str(i) for i in c[idx]) + '}' for c in comps)
