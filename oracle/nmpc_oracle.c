@@ -33,7 +33,8 @@
 enum { MODEL_FORCE = 0, MODEL_JERK = 1, MODEL_PLANT = 2, MODEL_ATT = 3 };
 /* MODEL_ATT (NOT in the reference; the north-star's 3-D attitude-and-total-thrust model): x = (p, v, q) with
  * the attitude quaternion q = (w, x, y, z) body->world, u = (T, wx, wy, wz):  pdot = v, vdot = (T/m) R(q) e3 - g e3,
- * qdot = 1/2 q (x) (0, w).  The planar plant of src/plant.py:27-33 is its restriction to the x-z plane. */
+ * qdot = 1/2 q (x) (0, w).  The planar plant of src/plant.py:27-33 is its restriction to the x-z plane.  PARITY UNPINNED for
+ * this model: the reference holds no run of it; the two oracles check each other (tests/test_att.py). */
 
 typedef struct {
     int model;         /* MODEL_FORCE | MODEL_JERK */
