@@ -424,16 +424,53 @@ def run_e2e(args, pkg, dev, local, inp, ref_im, world, barrier, allmax, Ke):
 
     dt_calls = run(step_calls)
     x_calls = xs_h.clone()
-    dt = run(step_fused)
-    same = float((x0b[(W + Ke) % 2][:, :4] - x_calls).abs().max())     # both paths walked the same closed loop
+    dt_one = run(step_fused)
+    x_one = x0b[(W + Ke) % 2].clone()
+    same = float((x_one[:, :4] - x_calls).abs().max())                 # both paths walked the same closed loop
+    s = None                                                            # (frees the single solver's workspace)
+    upf = pin(B, 2)
+
+    # ---- the same step for the fleet split into G solver objects on G streams (SolverFleet): a sub-fleet is synchronised
+    #      only right before its own next step is enqueued, so the tail of one launch overlaps the next sub-fleet's launch
+    G = max(1, min(args.e2e_groups, B))
+    fleet = pkg.SolverFleet(args.model, batch=B, groups=G, device=local, precision=args.precision, N_horizon=N, rti=args.rti)
+    bad_steps = [0]
+
+    def on_results(g, lo, hi):                                          # the reference's status check, per sub-fleet
+        bad_steps[0] += int((st_host[lo:hi] != 0).sum())
+
+    def run_fleet():
+        fleet.reset()
+        x0b[0][:, :4] = inp['x0'].t()
+        if jerk:
+            x0b[0][:, 4] = 0.0; x0b[0][:, 5] = 9.81
+        for i in range(W):
+            fleet.step(yh[i], x0b[i % 2], noise_h[i], u_host, upf, st_host, x0b[(i + 1) % 2])
+        fleet.synchronize()
+        bad_steps[0] = 0
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(W, W + Ke):
+            fleet.step(yh[i], x0b[i % 2], noise_h[i], u_host, upf, st_host, x0b[(i + 1) % 2], on_results=on_results)
+        fleet.synchronize(on_results=on_results)
+        barrier()
+        return allmax(time.perf_counter() - t0)
+
+    dt = run_fleet()
+    same_fleet = float((x0b[(W + Ke) % 2] - x_one).abs().max())          # identical to the single solver object (bit for bit)
     bad = int((st_host != 0).sum())
     return {'value': world * B * Ke / dt, 'unit': UNIT, 'steps': Ke, 'ms_per_step': dt / Ke * 1e3,
             'h2d_bytes_per_step': int(B * (per + nx + 1) * 8), 'd2h_bytes_per_step': int(B * (nu * 8 + 2 * 8 + 4 + nx * 8)),
-            'nonzero_status_last_step': bad,
-            'api': 'per control step, pinned host buffers: BatchedAcadosOcpSolver.set_yref_all (OCP.set_up_ocp: the yref window, H2D) + '
-                   'step_into = bnmpc_step_for_x0 (x0 and the noise draw in; x0 embedding, solve, get(0,u), Converter.convert and '
-                   'simulate_next_x on the device; u0, u_plant, status and the next x0 out).  The upload of the next step\'s window '
-                   '(known in advance) rides a copy stream behind this step\'s x0 and overlaps the solve',
+            'nonzero_status_last_step': bad, 'nonzero_status_steps_seen_by_host': bad_steps[0], 'groups': G,
+            'api': f'per control step, pinned host buffers, SolverFleet of {G} solver objects on {G} streams (sub-fleets of {B // G} drones, '
+                   'software-pipelined: a sub-fleet is synchronised - and its statuses checked on the host - right before its own next step '
+                   'is enqueued); per sub-fleet BatchedAcadosOcpSolver.set_yref_all (OCP.set_up_ocp: the yref window, H2D) + step_into = '
+                   'bnmpc_step_for_x0 (x0 and the noise draw in; x0 embedding, solve, get(0,u), Converter.convert and simulate_next_x on the '
+                   'device; u0, u_plant, status and the next x0 out)',
+            'max_abs_state_difference_to_single_solver': same_fleet,
+            'single_solver': {'value': world * B * Ke / dt_one, 'unit': UNIT, 'ms_per_step': dt_one / Ke * 1e3,
+                              'api': 'the same calls on ONE solver object for the whole batch, synchronised every step; the upload of the '
+                                     'next step\'s window rides a copy stream behind this step\'s x0'},
             'reference_call_sequence': {'value': world * B * Ke / dt_calls, 'unit': UNIT, 'ms_per_step': dt_calls / Ke * 1e3,
                                         'h2d_bytes_per_step': int(B * (per + nx + 4 + 2 * nsub + 1) * 8),
                                         'd2h_bytes_per_step': int(B * (nu * 8 + 4 + 4 * 8)),
@@ -616,6 +653,7 @@ def main():
     ap.add_argument('--skip-cpu', action='store_true')
     ap.add_argument('--skip-extra', action='store_true')
     ap.add_argument('--e2e-steps', type=int, default=50)
+    ap.add_argument('--e2e-groups', type=int, default=4, help='solver objects (streams) the e2e leg splits the batch into (SolverFleet)')
     ap.add_argument('--cpu-instances', type=int, default=4096)
     ap.add_argument('--cpu-steps', type=int, default=400, help='closed-loop steps of the cpu_baseline sample (~10-20 s of CPU work on 16 cores)')
     args = ap.parse_args()

@@ -744,3 +744,57 @@ def test_one_call_control_step_matches_the_fused_loop(model):
     X = np.stack(X, 1)
     np.testing.assert_allclose(X, want['Xsim'], rtol=0, atol=1e-9)
     np.testing.assert_allclose(X, fused['Xsim'], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize('model,groups', [('force', 3), ('jerk', 4)])
+def test_solver_fleet_pipeline_matches_one_solver_and_the_oracle(model, groups):
+    """SolverFleet: the batch split into G solver objects on G streams, stepped as a software pipeline (a sub-fleet is
+    synchronised only before its own next step).  Same closed loop as the oracle; the host hook sees every step's results
+    of every drone exactly once, before that drone's next step is enqueued."""
+    B, S = 50, 8
+    om = MODEL_ID[model]
+    refs, x0, noise, pc, pp = random_loop_inputs(B, S, seed=71 + om, mass_sigma=0.05)
+    want = co.closed_loop(co.default_opts(om), refs, x0, noise, pc, pp, S)
+    fleet = pkg.SolverFleet(model, batch=B, groups=groups, device=0)
+    assert fleet.groups == groups and fleet.slices()[0][0] == 0 and fleet.slices()[-1][1] == B
+    nx, nu, N, ny = fleet.nx, fleet.nu, fleet.N, fleet.ny
+    pin = lambda *sh, dt=torch.float64: torch.zeros(sh, dtype=dt).pin_memory()
+    xb, u0, up, st = [pin(B, nx), pin(B, nx)], pin(B, nu), pin(B, 2), pin(B, dt=torch.int32)
+    ppt = torch.tensor(pp).pin_memory()
+    eps = torch.tensor(noise).pin_memory()
+    xb[0][:, :4] = torch.tensor(x0)
+    if nx == 6:
+        xb[0][:, 4] = 0.0; xb[0][:, 5] = 9.81
+    cols = list(range(8)) if nx == 6 else list(range(6))
+    ys = [torch.tensor(np.concatenate([refs[:, i:i + N, cols].reshape(B, N * ny), refs[:, i + N, :nx]], 1)).pin_memory() for i in range(S)]
+    seen = {'st': [], 'u': [], 'x': []}
+    step_of = [0] * groups
+
+    def on_results(g, lo, hi):
+        i = step_of[g]
+        step_of[g] += 1
+        seen['st'].append((i, lo, hi, st[lo:hi].numpy().copy()))
+        seen['u'].append((i, lo, hi, u0[lo:hi].numpy().copy()))
+        seen['x'].append((i, lo, hi, xb[(i + 1) % 2][lo:hi, :4].numpy().copy()))
+
+    for i in range(S):
+        fleet.step(ys[i], xb[i % 2], eps[i], u0, up, st, xb[(i + 1) % 2], p_plant=ppt, on_results=on_results)
+    fleet.synchronize(on_results=on_results)
+    assert step_of == [S] * groups
+    for i, lo, hi, v in seen['st']:
+        assert np.array_equal(v, want['status'][lo:hi, i])
+    for i, lo, hi, v in seen['u']:
+        np.testing.assert_allclose(v, want['U_ctrl'][lo:hi, i], rtol=0, atol=1e-9)
+    for i, lo, hi, v in seen['x']:
+        np.testing.assert_allclose(v, want['Xsim'][lo:hi, i + 1], rtol=0, atol=1e-9)
+    # one solver object for the whole batch walks the same loop bit for bit
+    s = pkg.BatchedAcadosOcpSolver(model, batch=B, device=0, numpy_io=False)
+    xa, xn = pin(B, nx), pin(B, nx)
+    xa[:, :4] = torch.tensor(x0)
+    if nx == 6:
+        xa[:, 4] = 0.0; xa[:, 5] = 9.81
+    for i in range(S):
+        s.set_yref_all(ys[i])
+        s.step_into(xa, eps[i], u0, up, st, xn, p_plant_host=ppt)
+        xa, xn = xn, xa
+    assert torch.equal(xa, xb[S % 2])

@@ -103,3 +103,17 @@ def test_trajectory_families_shapes_and_formulas():
         np.testing.assert_allclose(sq[b, 2 * side, :2], initial[b] + [L, L], atol=1e-15)
         np.testing.assert_allclose(sq[b, 3 * side + 1, :2], initial[b] + [0, L - L / side], atol=1e-15)
         np.testing.assert_allclose(sq[b, N:], sq[b, :NH], atol=0)
+
+
+def test_fleet_group_bounds():
+    """SolverFleet's slices: contiguous, cover the batch, sizes differ by at most one, never more groups than drones."""
+    from drone_attitude_control_b200.fleet import group_bounds
+    assert group_bounds(4096, 4) == [0, 1024, 2048, 3072, 4096]
+    assert group_bounds(10, 3) == [0, 4, 7, 10]
+    assert group_bounds(2, 5) == [0, 1, 2]
+    for B, G in [(1, 1), (7, 7), (4097, 4), (50, 3)]:
+        b = group_bounds(B, G)
+        sizes = np.diff(b)
+        assert b[0] == 0 and b[-1] == B and sizes.min() >= 1 and sizes.max() - sizes.min() <= 1
+    with pytest.raises(ValueError):
+        group_bounds(0, 2)

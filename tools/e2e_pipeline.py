@@ -37,9 +37,7 @@ class Sub:
         self.yev = [torch.cuda.Event(), torch.cuda.Event()]
 
     def prefetch(self, i):
-        with torch.cuda.stream(self.copy_stream):
-            self.ydev[i % 2].copy_(self.yh[i], non_blocking=True)
-            self.yev[i % 2].record(self.copy_stream)
+        pass
 
     def start(self):
         with torch.cuda.stream(self.stream):
@@ -48,12 +46,8 @@ class Sub:
         self.prefetch(0)
 
     def enqueue(self, i, last):
-        with torch.cuda.stream(self.stream):
-            self.stream.wait_event(self.yev[i % 2])
-            self.s.set_yref_all(self.ydev[i % 2])
-            self.s.step_into(self.x0b[i % 2], self.noise[i], self.u, self.up, self.st, self.x0b[(i + 1) % 2], wait=False)
-        if not last:
-            self.prefetch(i + 1)
+        self.s.set_yref_all(self.yh[i])          # pinned host window -> H2D on the sub-fleet's own stream
+        self.s.step_into(self.x0b[i % 2], self.noise[i], self.u, self.up, self.st, self.x0b[(i + 1) % 2], wait=False)
 
 
 for G in Gs:
