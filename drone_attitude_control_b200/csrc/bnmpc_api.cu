@@ -577,8 +577,13 @@ int bnmpc_create(const bnmpc_config* cfg, int batch, int device, void** handle) 
         // warps per instance of the closed-loop kernel: with few instances per SM (long horizon, or a small batch spread over
         // the SMs) each one gets a group of 2 or 4 warps for its 32-lane passes, up to the launch bound and the tensor memory
         wpg = 1;
-        for (int g = ops->max_wpg; g >= 2; g /= 2)
-            if (warps * g <= ops->max_warps && ops->tmem_cols(cfg->horizon, warps * g, g) != 0) { wpg = g; break; }
+        int optin = 0;
+        CKH(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        for (int g = ops->max_wpg; g >= 2; g /= 2) {
+            const long stat = ops->loop_static_bytes(g);           // (the group kernels carry the scans' exchange area)
+            if (warps * g <= ops->max_warps && ops->tmem_cols(cfg->horizon, warps * g, g) != 0 && stat >= 0 &&
+                (size_t)warps * ops->smem_bytes(cfg->horizon) + (size_t)stat <= (size_t)optin) { wpg = g; break; }
+        }
         if (const char* e = getenv("BNMPC_WARPS_PER_INSTANCE")) {   // tuning knob: 1 switches the warp groups off
             const int v = atoi(e);
             if (v >= 1 && v < wpg) wpg = (v >= 2) ? 2 : 1;

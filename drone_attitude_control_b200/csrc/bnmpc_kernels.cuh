@@ -63,6 +63,7 @@ struct ModelOps {
     cudaError_t (*loop_ls)(const GsAny&, const Opts&, const LoopArgs&, int ctas, int warps, int* queue, cudaStream_t);
     // warps per CTA and warps per instance (wpg; instances in flight per SM = warps / wpg), warps = 0: does not fit
     cudaError_t (*cta_shape)(int N, int* warps, int* wpg);
+    long (*loop_static_bytes)(int wpg);                             // static shared memory of the closed-loop kernel (-1: none)
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -424,7 +425,11 @@ struct OpsImpl {
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - 1024);   // minus the static part
+        cudaFuncAttributes fa;
+        e = cudaFuncGetAttributes(&fa, kern);
+        if (e != cudaSuccess) return e;
+        const int stat = fa.sharedSizeBytes > 1024 ? (int)fa.sharedSizeBytes : 1024;                  // the static part (the 2- / 4-warp
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - stat);   // kernels carry the scans' exchange area)
         if (e != cudaSuccess) return e;
         return cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     }
@@ -461,6 +466,20 @@ struct OpsImpl {
         int g = 1;
         *wpg = g;
         return cudaSuccess;
+    }
+    // static shared memory of the closed-loop kernel with wpg warps per instance (-1: no such kernel)
+    static long loop_static_bytes(int wpg) {
+        if constexpr (!LOOP) return -1;
+        else {
+            cudaFuncAttributes fa;
+            cudaError_t e = cudaErrorInvalidValue;
+            if (wpg == 1) e = cudaFuncGetAttributes(&fa, k_loop_step<M, T, 1>);
+            else if constexpr (GROUPS) {
+                if (wpg == 2) e = cudaFuncGetAttributes(&fa, k_loop_step<M, T, 2>);
+                else if (wpg == 4) e = cudaFuncGetAttributes(&fa, k_loop_step<M, T, 4>);
+            }
+            return e == cudaSuccess ? (long)fa.sharedSizeBytes : -1;
+        }
     }
     static cudaError_t solve(const GsAny& a, const Opts& o_, int ctas, int warps, int* queue, cudaStream_t st) {
         Opts o = o_;
@@ -501,7 +520,7 @@ struct OpsImpl {
     }
     static ModelOps make(int kind) {
         return ModelOps{M::name(), M::NX, M::NU, M::NP, M::NBLK, M::NXB, M::NUB, kind, M::JAC_CONST ? 1 : 0, (int)sizeof(T),
-                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, GROUPS ? 4 : 1, LaunchShape<M, T>::MAX_WARPS, &smem_bytes, &tmem_cols, &solve, &solve_sb, &loop_step, &loop_ls, &cta_shape};
+                        SmLayout<M, false, TmemPriv<M, T>::QB_PRIV>::ROWS, GROUPS ? 4 : 1, LaunchShape<M, T>::MAX_WARPS, &smem_bytes, &tmem_cols, &solve, &solve_sb, &loop_step, &loop_ls, &cta_shape, &loop_static_bytes};
     }
 };
 
