@@ -495,7 +495,7 @@ def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):
             peak[prec] = tf.value
         return peak[prec]
 
-    def one(model, total, N, prec, steps, warm, mass_sigma, sharded, table=False):
+    def one(model, total, N, prec, steps, warm, mass_sigma, sharded, table=False, rti=False):
         lo, hi = shard_range(total, rank, world) if sharded else (rank * total, (rank + 1) * total)
         b = hi - lo
         inp = instance_inputs(lo, hi, 0, seed=SEED, mass_sigma=mass_sigma, with_noise=False)
@@ -507,7 +507,7 @@ def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):
             cref = pkg.CircleRef(inp['radius'], inp['center'], inp['phase'], n=500)
         r, ph, c = inp['radius'], inp['phase'], inp['center']
         x0 = torch.stack([c[:, 0] + r * torch.cos(ph), c[:, 1] + r * torch.sin(ph), -r * om * torch.sin(ph), r * om * torch.cos(ph)]) + inp['dx0']
-        loop = pkg.BatchedClosedLoop(model, batch=b, device=local, precision=prec, N_horizon=N)
+        loop = pkg.BatchedClosedLoop(model, batch=b, device=local, precision=prec, N_horizon=N, rti=rti)
         pp = torch.stack([0.03277 * inp['mass_scale'], torch.full((b,), 9.81, dtype=torch.float64)]) if mass_sigma > 0 else None
         loop.init(x0, cref, noise=pkg.PhiloxNoise(seed=SEED, std=0.01, first_instance=lo), p_plant=pp, n_steps=warm + steps, log=False)
         loop.run(warm, steps_per_launch=warm)
@@ -524,27 +524,31 @@ def run_extra(args, pkg, dev, local, rank, world, barrier, allmax, shard_range):
             dist.all_reduce(st)
         tot = int(st[3])
         nblk, n, m, nx, nu, erk = MODEL_DIMS[model]
-        fl = flops_per_solve(nblk, n, m, N, erk, float(st[1]) / tot, float(st[2]) / tot + 1.0) * tot * steps
+        fl = flops_per_solve(nblk, n, m, N, erk, float(st[1]) / tot, 1.0 if rti else float(st[2]) / tot + 1.0) * tot * steps
         ach = fl / (ms * 1e-3) * 1e-12
         del loop
         torch.cuda.empty_cache()
         return {'model': model, 'instances_total': tot, 'instances_this_rank': b, 'sharded_over_ranks': bool(sharded), 'horizon': N,
-                'precision': prec, 'steps': steps, 'warmup': warm, 'ms': ms, 'reference': 'tables in HBM' if table else 'generated in the kernel', 'value': tot * steps / (ms * 1e-3), 'unit': UNIT,
+                'precision': prec, 'nlp_solver': 'SQP_RTI' if rti else 'SQP', 'steps': steps, 'warmup': warm, 'ms': ms, 'reference': 'tables in HBM' if table else 'generated in the kernel', 'value': tot * steps / (ms * 1e-3), 'unit': UNIT,
                 'failed_steps': int(st[0]), 'qp_iter_mean_last_step': float(st[1]) / tot,
                 'roofline_frac': ach / fma_peak(prec), 'achieved_tflops': ach}
 
     out = {'note': 'multi-step launches (steps_per_launch = steps), noise drawn in the kernel (PhiloxNoise), reference tables in HBM (config 3) '
                    'or generated in the kernel (configs 4, 5), CUDA events, max over ranks'}
+    # the metric's name says SQP-RTI; the reference's OCP is configured nlp_solver_type = 'SQP' (src/force_model/ocp.py:83), which the
+    # headline follows - this is config 2 with one QP per control step (acados SQP_RTI), 4096 drones per GPU, tables in HBM
+    out['config2_force_4096_sqp_rti'] = one('force', 4096, 30, 'fp64', 100, 10, 0.0, False, table=True, rti=True)
     out['config3_jerk_16384_fp64'] = one('jerk', 16384, 30, 'fp64', 20, 5, 0.0, False, table=True)
     out['config3_jerk_16384_fp32'] = one('jerk', 16384, 30, 'fp32', 20, 5, 0.0, False, table=True)
     out['config4_force_262144_mass_perturbed_sharded'] = dict(one('force', 262144, 30, 'fp64', 10, 3, 0.05, True), scaling='strong')
     for N in (20, 50, 100):
         out[f'config5_force_65536_N{N}'] = one('force', 65536, N, 'fp64', 4 if N > 30 else 8, 2, 0.0, False)
     out['north_star_att_3d_nx10_nu4'] = att_extra(args, dev, local, rank, world, barrier, allmax)
+    out['north_star_att_3d_nx10_nu4_sqp_rti'] = att_extra(args, dev, local, rank, world, barrier, allmax, steps=12, warm=8, rti=True)
     return out
 
 
-def att_extra(args, dev, local, rank, world, barrier, allmax, per_rank=4736, steps=6, warm=4):
+def att_extra(args, dev, local, rank, world, barrier, allmax, per_rank=4736, steps=6, warm=4, rti=False):
     """The 3-D attitude-and-total-thrust OCP of the north-star (nx 10, nu 4; not in the reference): closed loop of `per_rank`
     drones per GPU on per-instance helix references with a 5 % plant-mass perturbation, device-resident, one
     bnmpc_step_for_x0 per control step (solve kernel + plant kernel); SQP to tolerance.  With --skip-cpu unset, rank 0 also
@@ -564,7 +568,8 @@ def att_extra(args, dev, local, rank, world, barrier, allmax, per_rank=4736, ste
     state = {}
 
     def run(first, n, x):
-        r = follow_trajectory_batched(ref[:, first:], x, n, p_plant=pp, device=local, log=True, solver=state.get('solver'))
+        kw = {} if 'solver' in state or not rti else {'rti': True}
+        r = follow_trajectory_batched(ref[:, first:], x, n, p_plant=pp, device=local, log=True, solver=state.get('solver'), **kw)
         state['solver'] = r['solver']
         return r
     r0 = run(0, warm, x0)                                     # warm-up: the cold-start solves
@@ -578,15 +583,16 @@ def att_extra(args, dev, local, rank, world, barrier, allmax, per_rank=4736, ste
         import torch.distributed as dist
         dist.all_reduce(st)
     tot = int(st[3])
-    out = {'model': 'att', 'instances_total': tot, 'horizon': 30, 'precision': 'fp64', 'steps': steps, 'warmup': warm, 'ms': ms,
+    perr = float((r1['Xsim'][:, 1:, :3] - ref[:, warm + 1:warm + steps + 1, :3]).norm(dim=2).mean())
+    out = {'model': 'att', 'nlp_solver': 'SQP_RTI' if rti else 'SQP', 'mean_position_error_m': perr, 'instances_total': tot, 'horizon': 30, 'precision': 'fp64', 'steps': steps, 'warmup': warm, 'ms': ms,
            'value': tot * steps / (ms * 1e-3), 'unit': UNIT, 'failed_steps': int(st[0]), 'qp_iter_mean': float(st[1]) / (tot * steps),
            'sqp_iter_mean': float(st[2]) / (tot * steps), 'launches_per_step': 2,
            'path': 'bnmpc_set_yref_all + bnmpc_step_for_x0 per control step, device buffers'}
-    fl = flops_per_solve(1, 10, 4, 30, 4, out['qp_iter_mean'], out['sqp_iter_mean'] + 1.0) * tot * steps
+    fl = flops_per_solve(1, 10, 4, 30, 4, out['qp_iter_mean'], 1.0 if rti else out['sqp_iter_mean'] + 1.0) * tot * steps
     out['achieved_tflops'] = fl / (ms * 1e-3) * 1e-12
     tf = C_peak(local)
     out['roofline_frac'] = out['achieved_tflops'] / tf if tf else None
-    if not args.skip_cpu and rank == 0:
+    if not args.skip_cpu and rank == 0 and not rti:
         import time
         from oracle import c_oracle as co
         ns = min(b, 8 * max(1, co.lib().orc_num_cores()))
