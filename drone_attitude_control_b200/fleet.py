@@ -36,20 +36,27 @@ class SolverFleet:
     lo_g:hi_g of them.  `x_next` of one step is meant to be passed as `x0` of the next (double-buffer it): the copies of a
     sub-fleet are ordered on its stream, so its next step may be enqueued before the host has looked at anything."""
 
-    def __init__(self, model='force', batch=1, groups=4, device=0, **solver_kw):
+    def __init__(self, model='force', batch=1, groups=4, device=0, solver_factory=None, **solver_kw):
+        """solver_factory(batch) -> solver object (default: a BatchedAcadosOcpSolver of `model` on a CUDA stream of its own);
+        anything with set_yref_all / step_into / synchronize / reset works (the CPU tests drive the pipeline with a recorder)."""
         self.bounds = group_bounds(batch, groups)
         self.groups = len(self.bounds) - 1
         self.batch = int(batch)
         self.solvers, self.streams = [], []
-        dev = torch.device('cuda', device) if not isinstance(device, torch.device) else device
         for g in range(self.groups):
+            b = self.bounds[g + 1] - self.bounds[g]
+            if solver_factory is not None:
+                self.solvers.append(solver_factory(b))
+                continue
+            dev = torch.device('cuda', device) if not isinstance(device, torch.device) else device
             st = torch.cuda.Stream(device=dev)
             with torch.cuda.stream(st):                     # the solver binds the current stream when it is created
-                s = BatchedAcadosOcpSolver(model, batch=self.bounds[g + 1] - self.bounds[g], device=device, numpy_io=False, **solver_kw)
+                s = BatchedAcadosOcpSolver(model, batch=b, device=device, numpy_io=False, **solver_kw)
             self.solvers.append(s)
             self.streams.append(st)
         s0 = self.solvers[0]
-        self.nx, self.nu, self.ny, self.ny_e, self.N, self.cfg = s0.nx, s0.nu, s0.ny, s0.ny_e, s0.N, s0.cfg
+        self.nx, self.nu, self.ny, self.ny_e, self.N = s0.nx, s0.nu, s0.ny, s0.ny_e, s0.N
+        self.cfg = getattr(s0, 'cfg', None)
         self._pending = [False] * self.groups
 
     def slices(self):

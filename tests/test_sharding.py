@@ -117,3 +117,60 @@ def test_fleet_group_bounds():
         assert b[0] == 0 and b[-1] == B and sizes.min() >= 1 and sizes.max() - sizes.min() <= 1
     with pytest.raises(ValueError):
         group_bounds(0, 2)
+
+
+def test_fleet_pipeline_order_on_cpu():
+    """SolverFleet's host logic with recording stand-ins for the solver objects: every sub-fleet gets its own rows of every
+    buffer, is synchronised exactly once per step and only right before its own next step is enqueued (the others are left
+    running), and the results hook sees each (sub-fleet, step) once, in step order, before that sub-fleet's next step."""
+    from drone_attitude_control_b200.fleet import SolverFleet
+    log = []
+
+    class Rec:
+        nx, nu, ny, ny_e, N = 4, 2, 6, 4, 30
+
+        def __init__(self, b):
+            self.b, self.id = b, len(made)
+            made.append(self)
+
+        def set_yref_all(self, y):
+            log.append(('yref', self.id, tuple(y.shape), float(y[0, 0])))
+
+        def step_into(self, x0, eps, u0, up, st, xn, p_plant_host=None, wait=True):
+            assert not wait and x0.shape[0] == self.b and xn.shape[0] == self.b and (eps is None or eps.shape[0] == self.b)
+            log.append(('step', self.id, float(x0[0, 0])))
+            xn.copy_(x0 + 1.0)              # "plant": next state = state + 1
+            st.fill_(self.id)
+
+        def synchronize(self):
+            log.append(('sync', self.id))
+
+        def reset(self):
+            log.append(('reset', self.id))
+
+    made = []
+    B, G, S = 10, 3, 4
+    fleet = SolverFleet(batch=B, groups=G, solver_factory=Rec)
+    assert fleet.slices() == [(0, 4), (4, 7), (7, 10)] and [r.b for r in made] == [4, 3, 3]
+    xb = [torch.zeros(B, 4, dtype=torch.float64), torch.zeros(B, 4, dtype=torch.float64)]
+    xb[0][:, 0] = torch.arange(B, dtype=torch.float64) * 100
+    u0, up, st = torch.zeros(B, 2), torch.zeros(B, 2), torch.zeros(B, dtype=torch.int32)
+    seen = []
+    for i in range(S):
+        y = torch.full((B, 30 * 6 + 4), float(i), dtype=torch.float64)
+        fleet.step(y, xb[i % 2], None, u0, up, st, xb[(i + 1) % 2], on_results=lambda g, lo, hi: seen.append((g, lo, hi, len([e for e in log if e[0] == 'step' and e[1] == g]))))
+    fleet.synchronize(on_results=lambda g, lo, hi: seen.append((g, lo, hi, S)))
+    # each sub-fleet: yref, step per control step; a sync before every step but the first, and one at the end
+    for g in range(G):
+        mine = [e[0] for e in log if e[1] == g]
+        assert mine == ['yref', 'step'] + ['sync', 'yref', 'step'] * (S - 1) + ['sync']
+    # round-robin: the sync of sub-fleet g at step i comes after the enqueue of sub-fleet g-1 at step i (the others keep running)
+    order = [(e[0], e[1]) for e in log if e[0] in ('sync', 'step')]
+    assert order[:G] == [('step', 0), ('step', 1), ('step', 2)] and order[G:G + 4] == [('sync', 0), ('step', 0), ('sync', 1), ('step', 1)]
+    # the hook saw every (sub-fleet, step) once, after exactly that many steps of the sub-fleet had been enqueued
+    assert sorted(seen) == sorted((g, lo, hi, k) for g, (lo, hi) in enumerate(fleet.slices()) for k in range(1, S + 1))
+    # the rows travelled through the right slices: S plant steps of +1 on every drone, statuses = sub-fleet id
+    assert torch.equal(xb[S % 2][:, 0], torch.arange(B, dtype=torch.float64) * 100 + S)
+    assert st.tolist() == [0] * 4 + [1] * 3 + [2] * 3
+    fleet.reset()
+    assert [e for e in log[-G:]] == [('reset', 0), ('reset', 1), ('reset', 2)]
