@@ -191,6 +191,24 @@ def test_att_closed_loop_matches_oracle():
 
 
 @pytest.mark.gpu
+def test_att_closed_loop_sqp_rti_matches_oracle():
+    """the same closed loop with ONE QP per control step (acados SQP_RTI, the north-star's wording): status, iteration counts
+    and trajectory against the oracle run with rti"""
+    from drone_attitude_control_b200.attitude_model import follow_trajectory_batched
+    B, S = 24, 25
+    refs, x0, pc, pp = att_inputs(B, seed=13, rows=S + 30)
+    noise = np.random.default_rng(4).normal(0, 0.002, (S, B))
+    want = co.closed_loop_att(co.default_opts(co.MODEL_ATT, rti=True), refs, x0, noise, pc, pp, S)
+    got = follow_trajectory_batched(refs, x0, S, noise=noise, p_ctrl=pc, p_plant=pp, rti=True)
+    assert np.array_equal(got['status'].cpu().numpy(), want['status']) and (want['status'] == 0).all()
+    assert np.array_equal(got['sqp_iter'].cpu().numpy(), want['sqp_iter']) and want['sqp_iter'].max() == 1
+    assert np.array_equal(got['qp_iter'].cpu().numpy(), want['qp_iter'])
+    np.testing.assert_allclose(got['Xsim'].cpu().numpy(), want['Xsim'], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(got['U_ctrl'].cpu().numpy(), want['U_ctrl'], rtol=0, atol=1e-9)
+    assert np.abs(want['Xsim'][:, -1, :3] - refs[:, S, :3]).max() < 0.05          # and it tracks
+
+
+@pytest.mark.gpu
 def test_att_sim_solver_matches_oracle():
     import drone_attitude_control_b200 as pkg
     import torch
